@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the dsp_core hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload chain|src|eq|fft] [--clips C] [--dtype f32|f64]
+
+Default workload ("chain") is one wave of BASELINE.json's config C5 shaped like
+config C2: `--clips` (default 1024) synthetic clips of 10 s @ 44.1 kHz per GPU,
+SRC 160/147 -> six-band EQ -> non-overlapping 4096-point Hann magnitude
+spectra, float32.  A "step" is one pass of that chain over the wave.  The
+metric is Msamples/s = input samples consumed per second, whole job (all
+ranks).  `value` is timed with CUDA events, inputs resident in HBM; `e2e` is
+the same chain through the host-buffer C-ABI call (pinned host memory in,
+host memory out, copies inside the timed region).
+
+One JSON line is printed by rank 0.  `--impl reference` times the CPU oracle
+port of the reference's own algorithm (dense zero-stuffed convolution,
+lfilter cascade, recursive FFT) on all host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS_IN = 44100
+CLIP_SAMPLES = 441000          # 10 s @ 44.1 kHz
+L_UP, M_DOWN = 160, 147
+N_FFT = 4096
+GAINS = {"Sub-Bass": 6, "Bass": -3, "Low Mids": 4, "High Mids": -6, "Presence": 3, "Brilliance": -9}
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="chain", choices=["chain", "src", "eq", "fft"])
+    ap.add_argument("--clips", type=int, default=1024, help="clips (channels) per GPU per step")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------
+CPU_SAMPLE_SECONDS_OF_AUDIO = 0.25
+
+
+def _cpu_one_clip(seed):
+    import numpy as np
+    from oracle import dsp_oracle as o
+
+    n = int(FS_IN * CPU_SAMPLE_SECONDS_OF_AUDIO)
+    x = np.random.default_rng(seed).uniform(-0.5, 0.5, n).astype(np.float32)
+    y, fs2 = o.resample_reference_form(x, FS_IN, M_DOWN, L_UP)     # dense form, as dsp_core.py:148-170
+    z = o.equalizer(y, fs2, GAINS)
+    mags = o.frame_magnitudes(z, N_FFT)
+    return float(np.sum(mags)) + float(z[0])
+
+
+def cpu_reference_step(pool, cores):
+    """One bounded sample: every core runs the reference-form chain on one
+    0.25 s clip.  Returns (seconds, input samples processed)."""
+    t0 = time.perf_counter()
+    pool.map(_cpu_one_clip, range(cores))
+    dt = time.perf_counter() - t0
+    return dt, cores * int(FS_IN * CPU_SAMPLE_SECONDS_OF_AUDIO)
+
+
+def make_pool():
+    import multiprocessing as mp
+
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    cores = max(1, min(cores, 64))
+    ctx = mp.get_context("fork")
+    return ctx.Pool(cores), cores
+
+
+def cpu_baseline(repeats=2):
+    pool, cores = make_pool()
+    try:
+        cpu_reference_step(pool, cores)            # warm the workers
+        best = None
+        for _ in range(repeats):
+            dt, n = cpu_reference_step(pool, cores)
+            rate = n / dt / 1e6
+            best = rate if best is None or rate > best else best
+    finally:
+        pool.close()
+        pool.join()
+    return {"value": best, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} clips x {CPU_SAMPLE_SECONDS_OF_AUDIO} s @44.1 kHz, one per core: oracle port of the "
+                      "reference chain (dense zero-stuffed np.convolve SRC 160/147, lfilter EQ, recursive FFT 4096)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pool, cores = make_pool()
+    try:
+        for _ in range(max(args.warmup, 1)):
+            cpu_reference_step(pool, cores)
+        total_t, total_n = 0.0, 0
+        for _ in range(args.steps):
+            dt, n = cpu_reference_step(pool, cores)
+            total_t += dt
+            total_n += n
+    finally:
+        pool.close()
+        pool.join()
+    value = total_n / total_t / 1e6
+    line = {
+        "impl": "reference", "metric": "Msamples/s SRC->EQ->FFT chain", "value": value, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                         "sample": f"each step: {cores} clips x {CPU_SAMPLE_SECONDS_OF_AUDIO} s, one per core"},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+def workload_config(args):
+    return {
+        "workload": "C5 chain, one wave shaped as C2: clips x 10 s @44.1 kHz -> SRC 160/147 -> 6-band EQ "
+                    "(gains 6,-3,4,-6,3,-9 dB) -> 4096-pt Hann |FFT| frames",
+        "selected": args.workload, "clips_per_gpu": args.clips, "clip_samples": CLIP_SAMPLES,
+        "L": L_UP, "M": M_DOWN, "n_fft": N_FFT,
+        "l2": "inputs per step exceed the 126 MB L2 (no flush needed)",
+        "parallelism": f"channel-sharded x{args.gpus}, no collective",
+    }
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+
+    def _loop(self):
+        names = {
+            "hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+            "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80,
+        }
+        while not self._stop.is_set():
+            try:
+                if self._nvml:
+                    p = self._nvml
+                    self.samples.append(p.nvmlDeviceGetClockInfo(self._h, p.NVML_CLOCK_SM))
+                    r = p.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                        p, "nvmlDeviceGetCurrentClocksEventReasons") else p.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                else:
+                    out = subprocess.run(
+                        ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                         "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = out.strip().split(",")
+                    self.samples.append(int(a))
+                    self.max_mhz = int(b)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:
+        return None
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dsp_audio_project_b200 as pkg
+    from dsp_audio_project_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    # CPU baseline first: its worker pool is forked before any CUDA context exists
+    cpu_line = None
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        cpu_line = cpu_baseline()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    np_dt = np.float32 if args.dtype == "f32" else np.float64
+    t_dt = torch.float32 if args.dtype == "f32" else torch.float64
+    esize = 4 if args.dtype == "f32" else 8
+    clips = args.clips
+    chain = pkg.Chain(L_UP, M_DOWN, FS_IN, GAINS, n_fft=N_FFT, dtype=np_dt)
+    n_out = chain.out_len(CLIP_SAMPLES)
+    n_frames = n_out // N_FFT
+    bins = N_FFT // 2 + 1
+
+    gen = torch.Generator(device=dev).manual_seed(4 + rank)
+    x = (torch.rand((clips, CLIP_SAMPLES), generator=gen, device=dev, dtype=t_dt) - 0.5)
+
+    # persistent device buffers so every step reuses the same memory
+    y = torch.empty((clips, n_out), dtype=t_dt, device=dev)
+    z = torch.empty((clips, n_out), dtype=t_dt, device=dev)
+    mag = torch.empty((clips, n_frames, bins), dtype=t_dt, device=dev)
+
+    def step_chain():
+        chain.src.run(x, out=y)
+        chain.eq.run(y, out=z)
+        chain.fft.magnitudes(z, out=mag)
+
+    def step_src():
+        chain.src.run(x, out=y)
+
+    def step_eq():
+        chain.eq.run(y, out=z)
+
+    def step_fft():
+        chain.fft.magnitudes(z, out=mag)
+
+    step = {"chain": step_chain, "src": step_src, "eq": step_eq, "fft": step_fft}[args.workload]
+    step_chain()                      # populate y, z for the single-kernel workloads
+    torch.cuda.synchronize()
+    samples_per_step = {"chain": clips * CLIP_SAMPLES, "src": clips * CLIP_SAMPLES,
+                        "eq": clips * n_out, "fft": clips * n_frames * N_FFT}[args.workload]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    # per-kernel timing (same stream, events between the launches)
+    names = ["src", "eq", "fft"]
+    fns = [step_src, step_eq, step_fft]
+    per_kernel = {k: 0.0 for k in names}
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for it in range(args.steps):
+        evs[it][0].record()
+        for j, fn in enumerate(fns):
+            fn()
+            evs[it][j + 1].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    for it in range(args.steps):
+        for j, k in enumerate(names):
+            per_kernel[k] += evs[it][j].elapsed_time(evs[it][j + 1]) / args.steps
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * samples_per_step * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- e2e: host-buffer C-ABI call, copies inside the timed region -------
+    e2e = None
+    if not args.no_e2e and args.workload == "chain":
+        xh = torch.empty((clips, CLIP_SAMPLES), dtype=t_dt, pin_memory=True)
+        xh.copy_(x)
+        zh = torch.empty((clips, n_out), dtype=t_dt, pin_memory=True)
+        mh = torch.empty((clips, n_frames, bins), dtype=t_dt, pin_memory=True)
+        xa, za, ma = xh.numpy(), zh.numpy(), mh.numpy()
+        chain.run_host(xa, za, ma)                   # warm-up (allocations, clocks)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            chain.run_host(xa, za, ma)
+        dt_host = time.perf_counter() - t0
+        th = torch.tensor([dt_host], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        dt_host = float(th.item())
+        e2e = {"value": world * clips * CLIP_SAMPLES * e2e_steps / dt_host / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": clips * CLIP_SAMPLES * esize,
+               "d2h_bytes_per_step": (clips * n_out + clips * n_frames * bins) * esize,
+               "steps": e2e_steps, "ms_per_step": dt_host / e2e_steps * 1e3,
+               "api": "dspb200_chain_host_f32 (pinned host buffers, 3-stream slab pipeline)"}
+        # the host path must reproduce the device path bit for bit
+        if rank == 0:
+            e2e["matches_device_path"] = bool(torch.equal(zh[:4].to(dev), z[:4]))
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        alg_bytes = {
+            "src": esize * clips * (CLIP_SAMPLES + n_out),
+            "eq": esize * clips * 2 * n_out,
+            "fft": esize * clips * n_frames * (N_FFT + bins),
+        }
+        kernel_names = {"src": "src_tiled_kernel", "eq": "eq_scan_kernel", "fft": "fft_stockham_kernel"}
+        kernels = {}
+        for k in names:
+            gbs = alg_bytes[k] / (per_kernel[k] * 1e-3) / 1e9
+            kernels[k] = {"kernel": kernel_names[k], "ms": per_kernel[k], "algorithmic_bytes": alg_bytes[k],
+                          "achieved_gbs": gbs, "frac": gbs / peak, "traffic": traffic_from_profiles(kernel_names[k])}
+        dom = max(names, key=lambda k: per_kernel[k]) if args.workload == "chain" else args.workload
+        line = {
+            "metric": "Msamples/s SRC->EQ->FFT chain" if args.workload == "chain" else f"Msamples/s {args.workload}",
+            "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
+            "roofline": {"bound": "hbm", "kernel": kernels[dom]["kernel"], "achieved": kernels[dom]["achieved_gbs"],
+                         "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                         "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
+                         "ms_per_launch": kernels[dom]["ms"]},
+            "kernels": kernels,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": e2e,
+        }
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

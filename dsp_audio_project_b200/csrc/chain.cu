@@ -1,0 +1,193 @@
+// The app's cascade (app.py:161-167, :202-205) on a batch of clips:
+//   y = SRC(x);  z = EQ(y);  mag = |FFT(hann * frames(z))|
+// Device form: three kernels on one stream (y may live in scratch).  Host form:
+// channel slabs pipelined over three streams so the H2D copy of slab k+1, the
+// kernels of slab k and the D2H copies of slab k-1 overlap.
+#include <cstdlib>
+
+#include "internal.cuh"
+
+namespace dspb200 {
+
+static int64_t src_out_len(int L, int M, int64_t n_in) {
+  int T = 0;
+  int64_t P = 0, n_out = 0;
+  dspb200_src_geometry(L, M, n_in, &T, &P, &n_out);
+  return n_out;
+}
+
+struct ChainShape {
+  int L = 1, M = 1, n_fft = 0;
+  int64_t n_out = 0, n_frames = 0, bins = 0;
+  size_t y_bytes = 0, fft_ws = 0;
+};
+
+template <typename T>
+static int chain_shape(const dspb200_src_plan* src, const dspb200_fft_plan* fft, int64_t channels, int64_t n_in,
+                       ChainShape& s) {
+  int dt = DType<T>::id;
+  if (src) {
+    int d2;
+    DSP_TRY(src_plan_ratio(src, &s.L, &s.M, &d2));
+    DSP_CHECK(d2 == dt, "src plan dtype does not match");
+    s.n_out = src_out_len(s.L, s.M, n_in);
+  } else {
+    s.n_out = n_in;
+  }
+  s.y_bytes = static_cast<size_t>(round_up(static_cast<int64_t>(channels) * s.n_out * sizeof(T), 256));
+  if (fft) {
+    int d2;
+    DSP_TRY(fft_plan_info(fft, &s.n_fft, &d2));
+    DSP_CHECK(d2 == dt, "fft plan dtype does not match");
+    s.n_frames = s.n_out / s.n_fft;
+    s.bins = s.n_fft / 2 + 1;
+    DSP_TRY(dspb200_fft_workspace_bytes(fft, channels * s.n_frames, &s.fft_ws));
+  }
+  return DSPB200_OK;
+}
+
+template <typename T>
+static int chain_run(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                     const T* x, int64_t xs, int64_t channels, int64_t n_in, T* y, T* z, T* mag, void* ws,
+                     size_t ws_bytes, cudaStream_t stream) {
+  DSP_CHECK(channels >= 0 && n_in >= 1, "bad shape");
+  if (channels == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
+  ChainShape s;
+  DSP_TRY(chain_shape<T>(src, fft, channels, n_in, s));
+  unsigned char* wsp = static_cast<unsigned char*>(ws);
+  size_t used = 0;
+  const T* yp = x;
+  int64_t y_stride = xs;
+  if (src) {
+    T* ybuf = y;
+    if (!ybuf) {
+      DSP_CHECK(ws != nullptr && ws_bytes >= s.y_bytes, "workspace too small for the SRC scratch");
+      ybuf = reinterpret_cast<T*>(wsp);
+      used = s.y_bytes;
+    }
+    DSP_TRY(src_run<T>(src, x, xs, ybuf, s.n_out, channels, n_in, stream, -1));
+    yp = ybuf;
+    y_stride = s.n_out;
+  }
+  if (eq) {
+    DSP_CHECK(eq_plan_dtype(eq) == DType<T>::id, "eq plan dtype does not match");
+    DSP_TRY(eq_run<T>(eq, yp, y_stride, z, s.n_out, channels, s.n_out, stream));
+  } else {
+    DSP_CUDA(cudaMemcpy2DAsync(z, s.n_out * sizeof(T), yp, y_stride * sizeof(T), s.n_out * sizeof(T), channels,
+                               cudaMemcpyDeviceToDevice, stream));
+  }
+  if (fft && mag && s.n_frames > 0) {
+    DSP_CHECK(s.fft_ws == 0 || (ws != nullptr && ws_bytes >= used + s.fft_ws), "workspace too small for the FFT");
+    DSP_TRY(fftmag_run<T>(fft, z, s.n_out, s.n_out, 0, s.n_fft, s.n_frames, mag, s.bins, s.n_frames * s.bins,
+                          channels, wsp ? wsp + used : nullptr, s.fft_ws, stream));
+  }
+  return DSPB200_OK;
+}
+
+template <typename T>
+static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                      const T* x, int64_t channels, int64_t n_in, T* z, T* mag) {
+  DSP_CHECK(channels >= 0 && n_in >= 1, "bad shape");
+  if (channels == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
+  DSP_TRY(ensure_device());
+  int64_t slab = 64;
+  if (const char* e = getenv("DSPB200_CHAIN_SLAB")) {
+    const long v = atol(e);
+    if (v > 0) slab = v;
+  }
+  if (slab > channels) slab = channels;
+  ChainShape s;
+  DSP_TRY(chain_shape<T>(src, fft, slab, n_in, s));
+  const int vec = 16 / static_cast<int>(sizeof(T));
+  const int64_t xp = round_up(n_in, vec);
+  constexpr int kStreams = 3;
+  const int n_streams = static_cast<int>(ceil_div(channels, slab) < kStreams ? ceil_div(channels, slab) : kStreams);
+  cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+  T* dx[kStreams] = {nullptr, nullptr, nullptr};
+  T* dz[kStreams] = {nullptr, nullptr, nullptr};
+  T* dm[kStreams] = {nullptr, nullptr, nullptr};
+  void* dw[kStreams] = {nullptr, nullptr, nullptr};
+  const size_t ws_bytes = s.y_bytes + s.fft_ws;
+  const size_t mag_elems = static_cast<size_t>(slab) * s.n_frames * s.bins;
+  cudaError_t e = cudaSuccess;
+  int rc = DSPB200_OK;
+  for (int i = 0; i < n_streams && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&dx[i], static_cast<size_t>(slab) * xp * sizeof(T));
+    if (e == cudaSuccess) e = cudaMalloc(&dz[i], static_cast<size_t>(slab) * s.n_out * sizeof(T));
+    if (e == cudaSuccess && mag_elems && mag) e = cudaMalloc(&dm[i], mag_elems * sizeof(T));
+    if (e == cudaSuccess && ws_bytes) e = cudaMalloc(&dw[i], ws_bytes);
+  }
+  int k = 0;
+  for (int64_t c0 = 0; c0 < channels && e == cudaSuccess && rc == DSPB200_OK; c0 += slab, ++k) {
+    const int i = k % n_streams;
+    const int64_t nc = (channels - c0) < slab ? (channels - c0) : slab;
+    e = cudaMemcpy2DAsync(dx[i], xp * sizeof(T), x + c0 * n_in, n_in * sizeof(T), n_in * sizeof(T), nc,
+                          cudaMemcpyHostToDevice, st[i]);
+    if (e != cudaSuccess) break;
+    rc = chain_run<T>(src, eq, fft, dx[i], xp, nc, n_in, nullptr, dz[i], dm[i], dw[i], ws_bytes, st[i]);
+    if (rc != DSPB200_OK) break;
+    e = cudaMemcpyAsync(z + c0 * s.n_out, dz[i], static_cast<size_t>(nc) * s.n_out * sizeof(T),
+                        cudaMemcpyDeviceToHost, st[i]);
+    if (e == cudaSuccess && dm[i])
+      e = cudaMemcpyAsync(mag + c0 * s.n_frames * s.bins, dm[i],
+                          static_cast<size_t>(nc) * s.n_frames * s.bins * sizeof(T), cudaMemcpyDeviceToHost, st[i]);
+  }
+  for (int i = 0; i < n_streams; ++i) {
+    if (st[i]) {
+      cudaError_t e2 = cudaStreamSynchronize(st[i]);
+      if (e == cudaSuccess) e = e2;
+    }
+  }
+  for (int i = 0; i < kStreams; ++i) {
+    cudaFree(dx[i]); cudaFree(dz[i]); cudaFree(dm[i]); cudaFree(dw[i]);
+    if (st[i]) cudaStreamDestroy(st[i]);
+  }
+  if (e != cudaSuccess) return fail(DSPB200_ERR_CUDA, "chain host path: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+}  // namespace dspb200
+
+using namespace dspb200;
+
+extern "C" {
+
+int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_fft_plan* fft, int64_t channels,
+                                  int64_t n_in, int keep_y, size_t* bytes) {
+  DSP_CHECK(bytes != nullptr, "bytes is NULL");
+  DSP_CHECK(channels >= 0 && n_in >= 1, "bad shape");
+  int dtype = DSPB200_F32, L, M, nf;
+  if (src) DSP_TRY(src_plan_ratio(src, &L, &M, &dtype));
+  else if (fft) DSP_TRY(fft_plan_info(fft, &nf, &dtype));
+  ChainShape s;
+  if (dtype == DSPB200_F32) DSP_TRY(chain_shape<float>(src, fft, channels, n_in, s));
+  else DSP_TRY(chain_shape<double>(src, fft, channels, n_in, s));
+  *bytes = ((src && !keep_y) ? s.y_bytes : 0) + s.fft_ws;
+  return DSPB200_OK;
+}
+
+int dspb200_chain_run_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                          const float* x, int64_t xs, int64_t channels, int64_t n_in, float* y, float* z,
+                          float* mag, void* ws, size_t ws_bytes, void* stream) {
+  return chain_run<float>(src, eq, fft, x, xs, channels, n_in, y, z, mag, ws, ws_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+int dspb200_chain_run_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                          const double* x, int64_t xs, int64_t channels, int64_t n_in, double* y, double* z,
+                          double* mag, void* ws, size_t ws_bytes, void* stream) {
+  return chain_run<double>(src, eq, fft, x, xs, channels, n_in, y, z, mag, ws, ws_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+int dspb200_chain_host_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                           const float* x, int64_t channels, int64_t n_in, float* z, float* mag) {
+  return chain_host<float>(src, eq, fft, x, channels, n_in, z, mag);
+}
+int dspb200_chain_host_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                           const double* x, int64_t channels, int64_t n_in, double* z, double* mag) {
+  return chain_host<double>(src, eq, fft, x, channels, n_in, z, mag);
+}
+
+}  // extern "C"

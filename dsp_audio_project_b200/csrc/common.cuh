@@ -1,0 +1,149 @@
+// Shared helpers for libdspb200: error plumbing, launch accounting, small
+// device utilities (cp.async, mbarrier, TMA, packed-fp32 FMA).  sm_100a only.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/dspb200.h"
+
+namespace dspb200 {
+
+// ---- error handling ------------------------------------------------------
+std::string& last_error();
+int fail(int code, const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define DSP_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return ::dspb200::fail(DSPB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call,          \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);              \
+  } while (0)
+
+#define DSP_CHECK(cond, ...)                                                            \
+  do {                                                                                  \
+    if (!(cond)) return ::dspb200::fail(DSPB200_ERR_INVALID, __VA_ARGS__);              \
+  } while (0)
+
+#define DSP_TRY(expr)                                                                   \
+  do {                                                                                  \
+    int rc__ = (expr);                                                                  \
+    if (rc__ != DSPB200_OK) return rc__;                                                \
+  } while (0)
+
+inline int after_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(DSPB200_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return DSPB200_OK;
+}
+
+int ensure_device();            // checks a usable sm_100 device is current
+int sm_count();                 // SMs of the current device (cached per device)
+int max_smem_optin();           // opt-in shared memory per block
+
+template <typename T> struct DType;
+template <> struct DType<float> { static constexpr int id = DSPB200_F32; };
+template <> struct DType<double> { static constexpr int id = DSPB200_F64; };
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// TMA descriptor encode (driver entry point fetched through the runtime, so
+// the library does not link libcuda).
+int encode_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t dim0, uint64_t dim1,
+                   uint64_t stride1_bytes, uint32_t box0, uint32_t box1);
+
+#ifdef __CUDACC__
+// ---- device utilities ----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte async copy global->shared; bytes beyond src_bytes are zero-filled.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// mbarrier + TMA (cp.async.bulk.tensor) -- the Blackwell/Hopper async-proxy path.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// Packed fp32 FMA (Blackwell FFMA2): d.xy += a.xy * s  with a scalar s that
+// ptxas folds into the instruction's broadcast operand (no extra MOV).
+__device__ __forceinline__ void ffma2_bcast(float2& d, const float2 a, const float s) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const float2 sv = make_float2(s, s);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(dd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&sv)));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(dd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+#endif  // __CUDACC__
+
+}  // namespace dspb200

@@ -1,0 +1,466 @@
+// K2 -- biquad equaliser cascade as a chunked parallel linear-recurrence scan.
+//
+// Replaces sistema_ecualizador / aplicar_ecuacion_diferencias
+// (dsp_core.py:205-254): up to 6 (here: up to 16) second-order sections in
+// series, zero initial state, one clip at the end (:254).
+//
+// Layout and mapping.  x, z: [channels, time], time fastest.  One WARP owns one
+// channel and marches over it in tiles of 32*LC samples (LC = 32 fp32 / 16
+// fp64).  A tile is staged global->shared with 16-byte cp.async (coalesced,
+// double buffered); lane l then owns the LC consecutive samples
+// [l*LC, (l+1)*LC) of the tile in registers.  For each section, in order:
+//   1. zero-state pass over the lane's chunk in the 2x2 state-space form
+//      (design.cu: rotation-scaling for complex poles, Schur form for real);
+//   2. warp-shuffle Kogge-Stone prefix composition of the chunk end states:
+//      f_l <- f_l + A^(LC*2^d) f_(l-2^d); the tile's carry-in state is folded
+//      into lane 0 first, so the inclusive result is the true state at the end
+//      of every chunk and lane 31's becomes the next tile's carry;
+//   3. correction y[i] += (c A^i) . q_in for the lane's true initial state.
+// All sections are applied to the register-resident chunk before it is
+// written back: the cascade costs ONE read and ONE write of HBM per sample.
+//
+// Roofline: 2*sizeof(T) algorithmic bytes per sample; ~8 FMA per section per
+// sample (6 zero-state + 2 correction), i.e. ~50 FMA/sample for six sections.
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "design.cuh"
+#include "internal.cuh"
+
+namespace dspb200 {
+
+constexpr int kEqPassSections = 8;   // sections fused per kernel launch
+constexpr int kEqWarpsPerCta = 8;
+
+template <typename T> struct EqCfg;
+template <> struct EqCfg<float> { static constexpr int LC = 32; static constexpr int PAD = 4; };
+template <> struct EqCfg<double> { static constexpr int LC = 16; static constexpr int PAD = 2; };
+
+template <typename T, int NS> struct EqKernelParams {
+  static constexpr int LC = EqCfg<T>::LC;
+  T a[NS][4];
+  T b[NS][2];
+  T c[NS][2];
+  T dd[NS];
+  T g[NS][LC][2];   // c * A^i, i = 0..LC-1
+  T pw[NS][5][4];   // A^(LC * 2^d), d = 0..4
+  T gain;
+  int clip;
+};
+
+template <typename T> struct EqKernelParams<T, 0> {
+  T gain;
+  int clip;
+};
+
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// kPlain: every section has b = [1, 0] and its direct gain folded into `gain`.
+template <typename T, int NS, bool kPlain>
+__global__ void __launch_bounds__(kEqWarpsPerCta * 32)
+eq_scan_kernel(const __grid_constant__ EqKernelParams<T, NS> p, const T* __restrict__ x,
+               long long x_stride, T* __restrict__ z, long long z_stride, long long channels,
+               long long n, int aligned) {
+  constexpr int LC = EqCfg<T>::LC;
+  constexpr int PITCH = LC + EqCfg<T>::PAD;        // chunk pitch: conflict-free 16-byte lane access
+  constexpr int VEC = 16 / static_cast<int>(sizeof(T));   // elements per 16 bytes
+  constexpr int TILE = 32 * LC;
+  constexpr int PIECES = TILE / VEC / 32;          // 16-byte pieces per lane per tile
+  constexpr int STAGE = 32 * PITCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  T* buf = reinterpret_cast<T*>(smem_raw) + static_cast<size_t>(warp) * 2 * STAGE;
+  const long long warps_total = static_cast<long long>(gridDim.x) * kEqWarpsPerCta;
+  const long long n_tiles = (n + TILE - 1) / TILE;
+
+  for (long long ch = static_cast<long long>(blockIdx.x) * kEqWarpsPerCta + warp; ch < channels;
+       ch += warps_total) {
+    const T* xc = x + ch * x_stride;
+    T* zc = z + ch * z_stride;
+    T carry[NS > 0 ? NS : 1][2];
+#pragma unroll
+    for (int s = 0; s < (NS > 0 ? NS : 1); ++s) carry[s][0] = carry[s][1] = T(0);
+
+    auto stage_in = [&](long long t, int st) {
+      T* dst = buf + st * STAGE;
+      const long long base = t * TILE;
+      if (aligned) {
+#pragma unroll
+        for (int k = 0; k < PIECES; ++k) {
+          const int q = lane + 32 * k;                  // piece index in the tile
+          const int e = q * VEC;                        // first element of the piece
+          const long long gi = base + e;
+          long long rem = (n - gi) * static_cast<long long>(sizeof(T));
+          const int nbytes = rem >= 16 ? 16 : (rem > 0 ? static_cast<int>(rem) : 0);
+          const T* src = nbytes > 0 ? xc + gi : xc;
+          cp_async16(dst + (e / LC) * PITCH + (e % LC), src, nbytes);
+        }
+      } else {
+        for (int e = lane; e < TILE; e += 32) {
+          const long long gi = base + e;
+          dst[(e / LC) * PITCH + (e % LC)] = gi < n ? xc[gi] : T(0);
+        }
+      }
+      cp_async_commit();
+    };
+
+    if (n_tiles > 0) stage_in(0, 0);
+    for (long long t = 0; t < n_tiles; ++t) {
+      const int st = static_cast<int>(t & 1);
+      if (t + 1 < n_tiles) {
+        stage_in(t + 1, st ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      T* cur = buf + st * STAGE + lane * PITCH;
+      T v[LC];
+#pragma unroll
+      for (int i = 0; i < LC; i += VEC) {
+        if constexpr (sizeof(T) == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(cur + i);
+          v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+        } else {
+          const double2 q = *reinterpret_cast<const double2*>(cur + i);
+          v[i] = q.x; v[i + 1] = q.y;
+        }
+      }
+
+      if constexpr (NS > 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const T a00 = p.a[s][0], a01 = p.a[s][1], a10 = p.a[s][2], a11 = p.a[s][3];
+        const T c0 = p.c[s][0], c1 = p.c[s][1];
+        T q0 = T(0), q1 = T(0);
+        // 1. zero-state pass
+#pragma unroll
+        for (int i = 0; i < LC; ++i) {
+          const T xi = v[i];
+          T y, n0, n1;
+          if constexpr (kPlain) {
+            y = fma_t(c0, q0, fma_t(c1, q1, xi));
+            n0 = fma_t(a00, q0, fma_t(a01, q1, xi));
+            n1 = fma_t(a10, q0, a11 * q1);
+          } else {
+            y = fma_t(c0, q0, fma_t(c1, q1, p.dd[s] * xi));
+            n0 = fma_t(a00, q0, fma_t(a01, q1, p.b[s][0] * xi));
+            n1 = fma_t(a10, q0, fma_t(a11, q1, p.b[s][1] * xi));
+          }
+          v[i] = y;
+          q0 = n0;
+          q1 = n1;
+        }
+        // 2. prefix composition of chunk end states across the warp
+        if (lane == 0) {
+          const T s0 = carry[s][0], s1 = carry[s][1];
+          q0 += fma_t(p.pw[s][0][0], s0, p.pw[s][0][1] * s1);
+          q1 += fma_t(p.pw[s][0][2], s0, p.pw[s][0][3] * s1);
+        }
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+          const T u0 = __shfl_up_sync(0xffffffffu, q0, 1 << d);
+          const T u1 = __shfl_up_sync(0xffffffffu, q1, 1 << d);
+          if (lane >= (1 << d)) {
+            q0 += fma_t(p.pw[s][d][0], u0, p.pw[s][d][1] * u1);
+            q1 += fma_t(p.pw[s][d][2], u0, p.pw[s][d][3] * u1);
+          }
+        }
+        T e0 = __shfl_up_sync(0xffffffffu, q0, 1);
+        T e1 = __shfl_up_sync(0xffffffffu, q1, 1);
+        if (lane == 0) { e0 = carry[s][0]; e1 = carry[s][1]; }
+        carry[s][0] = __shfl_sync(0xffffffffu, q0, 31);
+        carry[s][1] = __shfl_sync(0xffffffffu, q1, 31);
+        // 3. correction with the lane's true initial state
+#pragma unroll
+        for (int i = 0; i < LC; ++i) v[i] = fma_t(p.g[s][i][0], e0, fma_t(p.g[s][i][1], e1, v[i]));
+      }
+      }  // NS > 0
+
+      // overall gain, clip (dsp_core.py:254), back through shared memory
+#pragma unroll
+      for (int i = 0; i < LC; ++i) {
+        T y = v[i] * p.gain;
+        if (p.clip) y = y < T(-1) ? T(-1) : (y > T(1) ? T(1) : y);   // NaN passes through like np.clip
+        v[i] = y;
+      }
+#pragma unroll
+      for (int i = 0; i < LC; i += VEC) {
+        if constexpr (sizeof(T) == 4)
+          *reinterpret_cast<float4*>(cur + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        else
+          *reinterpret_cast<double2*>(cur + i) = make_double2(v[i], v[i + 1]);
+      }
+      __syncwarp();
+      const T* out = buf + st * STAGE;
+      const long long base = t * TILE;
+      if (aligned && base + TILE <= n) {
+#pragma unroll
+        for (int k = 0; k < PIECES; ++k) {
+          const int e = (lane + 32 * k) * VEC;
+          const T* sp = out + (e / LC) * PITCH + (e % LC);
+          if constexpr (sizeof(T) == 4)
+            *reinterpret_cast<float4*>(zc + base + e) = *reinterpret_cast<const float4*>(sp);
+          else
+            *reinterpret_cast<double2*>(zc + base + e) = *reinterpret_cast<const double2*>(sp);
+        }
+      } else {
+        for (int e = lane; e < TILE; e += 32) {
+          const long long gi = base + e;
+          if (gi < n) zc[gi] = out[(e / LC) * PITCH + (e % LC)];
+        }
+      }
+      __syncwarp();   // the stage is refilled two iterations from now
+    }
+  }
+}
+
+// ---- plan ------------------------------------------------------------------
+}  // namespace dspb200
+
+struct dspb200_eq_plan {
+  int dtype;
+  int clip;
+  int device;
+  std::vector<dspb200::Section> sections;
+};
+
+namespace dspb200 {
+
+template <typename T, int NS>
+static void fill_params(EqKernelParams<T, NS>& kp, const Section* sec, bool plain, bool clip) {
+  constexpr int LC = EqCfg<T>::LC;
+  double gain = 1.0;
+  for (int s = 0; s < NS; ++s) {
+    const Section& S = sec[s];
+    double c0 = S.c[0], c1 = S.c[1], dd = S.d;
+    if (plain) {  // fold the direct gain: y/d = (c/d) . q + x
+      gain *= S.d;
+      c0 /= S.d;
+      c1 /= S.d;
+      dd = 1.0;
+    }
+    for (int i = 0; i < 4; ++i) kp.a[s][i] = static_cast<T>(S.a[i]);
+    kp.b[s][0] = static_cast<T>(S.b0);
+    kp.b[s][1] = static_cast<T>(S.b1);
+    kp.c[s][0] = static_cast<T>(c0);
+    kp.c[s][1] = static_cast<T>(c1);
+    kp.dd[s] = static_cast<T>(dd);
+    for (int i = 0; i < LC; ++i) {
+      double m[4];
+      mat2_power(S.a, i, m);
+      kp.g[s][i][0] = static_cast<T>(c0 * m[0] + c1 * m[2]);
+      kp.g[s][i][1] = static_cast<T>(c0 * m[1] + c1 * m[3]);
+    }
+    for (int d = 0; d < 5; ++d) {
+      double m[4];
+      mat2_power(S.a, static_cast<long long>(LC) << d, m);
+      for (int i = 0; i < 4; ++i) kp.pw[s][d][i] = static_cast<T>(m[i]);
+    }
+  }
+  kp.gain = static_cast<T>(gain);
+  kp.clip = clip ? 1 : 0;
+}
+
+template <typename T, int NS, bool kPlain>
+static int launch_pass(const Section* sec, bool clip, const T* x, int64_t xs, T* z, int64_t zs,
+                       int64_t channels, int64_t n, cudaStream_t stream) {
+  constexpr int LC = EqCfg<T>::LC;
+  constexpr int PITCH = LC + EqCfg<T>::PAD;
+  EqKernelParams<T, NS> kp;
+  if constexpr (NS > 0) {
+    fill_params<T, NS>(kp, sec, kPlain, clip);
+  } else {
+    kp.gain = T(1);
+    kp.clip = clip ? 1 : 0;
+  }
+  const size_t smem = static_cast<size_t>(kEqWarpsPerCta) * 2 * 32 * PITCH * sizeof(T);
+  auto kern = eq_scan_kernel<T, NS, kPlain>;
+  DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int vec = 16 / static_cast<int>(sizeof(T));
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(z) % 16 == 0) &&
+                       (xs % vec == 0) && (zs % vec == 0);
+  const int64_t ctas_needed = ceil_div(channels, kEqWarpsPerCta);
+  const int64_t max_ctas = static_cast<int64_t>(sm_count()) * 2;
+  const int grid = static_cast<int>(ctas_needed < max_ctas ? ctas_needed : max_ctas);
+  kern<<<grid, kEqWarpsPerCta * 32, smem, stream>>>(kp, x, xs, z, zs, channels, n, aligned ? 1 : 0);
+  return after_launch("eq_scan_kernel");
+}
+
+template <typename T, bool kPlain>
+static int dispatch_ns(int ns, const Section* sec, bool clip, const T* x, int64_t xs, T* z, int64_t zs,
+                       int64_t channels, int64_t n, cudaStream_t stream) {
+  switch (ns) {
+    case 1: return launch_pass<T, 1, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    case 2: return launch_pass<T, 2, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    case 3: return launch_pass<T, 3, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    case 4: return launch_pass<T, 4, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    case 5: return launch_pass<T, 5, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    case 6: return launch_pass<T, 6, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    case 7: return launch_pass<T, 7, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    case 8: return launch_pass<T, 8, kPlain>(sec, clip, x, xs, z, zs, channels, n, stream);
+    default: return fail(DSPB200_ERR_INVALID, "internal: bad section count %d", ns);
+  }
+}
+
+template <typename T>
+int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs, int64_t channels,
+           int64_t n, cudaStream_t stream) {
+  DSP_CHECK(plan != nullptr, "plan is NULL");
+  DSP_CHECK(plan->dtype == DType<T>::id, "plan dtype %d does not match the entry point", plan->dtype);
+  DSP_CHECK(channels >= 0 && n >= 0, "negative shape");
+  if (channels == 0 || n == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
+  DSP_CHECK(xs >= n && zs >= n, "channel stride smaller than n");
+  DSP_TRY(ensure_device());
+  const int total = static_cast<int>(plan->sections.size());
+  if (total == 0)
+    return launch_pass<T, 0, true>(nullptr, plan->clip != 0, x, xs, z, zs, channels, n, stream);
+  const T* src = x;
+  int64_t src_stride = xs;
+  for (int first = 0; first < total; first += kEqPassSections) {
+    const int ns = (total - first) < kEqPassSections ? (total - first) : kEqPassSections;
+    const bool last = first + ns >= total;
+    const Section* sec = plan->sections.data() + first;
+    bool plain = true;
+    for (int s = 0; s < ns; ++s)
+      if (!sec[s].complex_poles || sec[s].d == 0.0 || !std::isfinite(1.0 / sec[s].d)) plain = false;
+    const bool clip = last && plan->clip != 0;
+    if (plain)
+      DSP_TRY((dispatch_ns<T, true>(ns, sec, clip, src, src_stride, z, zs, channels, n, stream)));
+    else
+      DSP_TRY((dispatch_ns<T, false>(ns, sec, clip, src, src_stride, z, zs, channels, n, stream)));
+    src = z;  // later passes run in place on the output
+    src_stride = zs;
+  }
+  return DSPB200_OK;
+}
+
+template int eq_run<float>(const dspb200_eq_plan*, const float*, int64_t, float*, int64_t, int64_t, int64_t, cudaStream_t);
+template int eq_run<double>(const dspb200_eq_plan*, const double*, int64_t, double*, int64_t, int64_t, int64_t, cudaStream_t);
+
+int eq_plan_dtype(const dspb200_eq_plan* plan) { return plan ? plan->dtype : -1; }
+
+template <typename T>
+static int eq_host(const dspb200_eq_plan* plan, const T* x, T* z, int64_t channels, int64_t n) {
+  DSP_CHECK(plan != nullptr, "plan is NULL");
+  DSP_CHECK(channels >= 0 && n >= 0, "negative shape");
+  if (channels == 0 || n == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
+  DSP_TRY(ensure_device());
+  const int vec = 16 / static_cast<int>(sizeof(T));
+  const int64_t pitch = round_up(n, vec);
+  T* d = nullptr;
+  DSP_CUDA(cudaMalloc(&d, static_cast<size_t>(channels) * pitch * sizeof(T)));
+  cudaStream_t st = nullptr;
+  int rc = DSPB200_OK;
+  cudaError_t e = cudaMemcpy2DAsync(d, pitch * sizeof(T), x, n * sizeof(T), n * sizeof(T), channels,
+                                    cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) rc = eq_run<T>(plan, d, pitch, d, pitch, channels, n, st);
+  if (e == cudaSuccess && rc == DSPB200_OK)
+    e = cudaMemcpy2DAsync(z, n * sizeof(T), d, pitch * sizeof(T), n * sizeof(T), channels,
+                          cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(DSPB200_ERR_CUDA, "eq host path: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+static int make_plan(std::vector<Section>&& secs, int clip, int dtype, dspb200_eq_plan** out) {
+  DSP_CHECK(out != nullptr, "plan output pointer is NULL");
+  DSP_CHECK(dtype == DSPB200_F32 || dtype == DSPB200_F64, "dtype must be 0 (f32) or 1 (f64)");
+  DSP_CHECK(secs.size() <= DSPB200_MAX_SECTIONS, "at most %d sections per plan", DSPB200_MAX_SECTIONS);
+  dspb200_eq_plan* p = new (std::nothrow) dspb200_eq_plan();
+  if (!p) return fail(DSPB200_ERR_ALLOC, "out of host memory");
+  p->dtype = dtype;
+  p->clip = clip ? 1 : 0;
+  p->device = -1;
+  p->sections = std::move(secs);
+  *out = p;
+  return DSPB200_OK;
+}
+
+}  // namespace dspb200
+
+using namespace dspb200;
+
+extern "C" {
+
+int dspb200_eq_plan_create(double fs, const double* fc_eff, const double* gains_db, int n_sections,
+                           int clip, int dtype, dspb200_eq_plan** plan) {
+  DSP_CHECK(n_sections >= 0, "n_sections must be >= 0");
+  DSP_CHECK(fs > 0.0, "fs must be positive");
+  DSP_CHECK(n_sections == 0 || (fc_eff && gains_db), "NULL section arrays");
+  std::vector<Section> secs;
+  for (int i = 0; i < n_sections; ++i) {
+    DSP_CHECK(fc_eff[i] > 0.0 && fc_eff[i] < fs / 2.0, "section %d: centre %g Hz outside (0, fs/2)", i, fc_eff[i]);
+    double b[3], a[3];
+    peaking_biquad(fc_eff[i], fs, gains_db[i], b, a);
+    secs.push_back(section_from_ba(b, a));
+  }
+  return make_plan(std::move(secs), clip, dtype, plan);
+}
+
+int dspb200_eq_plan_create_raw(const double* ba, int n_sections, int clip, int dtype,
+                               dspb200_eq_plan** plan) {
+  DSP_CHECK(n_sections >= 0, "n_sections must be >= 0");
+  DSP_CHECK(n_sections == 0 || ba != nullptr, "ba is NULL");
+  std::vector<Section> secs;
+  for (int i = 0; i < n_sections; ++i) {
+    const double* r = ba + 6 * i;
+    DSP_CHECK(r[3] != 0.0, "section %d: a0 must be non-zero", i);
+    secs.push_back(section_from_ba(r, r + 3));
+  }
+  return make_plan(std::move(secs), clip, dtype, plan);
+}
+
+int dspb200_eq_plan_create_bands(double fs, const double gains_db[DSPB200_EQ_BANDS], int dtype,
+                                 dspb200_eq_plan** plan, int* bypass) {
+  DSP_CHECK(gains_db != nullptr && bypass != nullptr, "NULL argument");
+  static const double centres[DSPB200_EQ_BANDS] = {40, 150, 1000, 3000, 5000, 10000};  // :225-228
+  double fc[DSPB200_EQ_BANDS], g[DSPB200_EQ_BANDS];
+  int n = 0;
+  DSP_TRY(dspb200_eq_select_sections(fs, centres, gains_db, DSPB200_EQ_BANDS, fc, g, &n, bypass));
+  if (*bypass) return make_plan({}, 0, dtype, plan);
+  return dspb200_eq_plan_create(fs, fc, g, n, 1, dtype, plan);
+}
+
+int dspb200_eq_plan_destroy(dspb200_eq_plan* plan) {
+  delete plan;
+  return DSPB200_OK;
+}
+
+int dspb200_eq_plan_describe(const dspb200_eq_plan* plan, int* n_sections, double* ss, int capacity) {
+  DSP_CHECK(plan != nullptr && n_sections != nullptr, "NULL argument");
+  *n_sections = static_cast<int>(plan->sections.size());
+  for (int i = 0; i < *n_sections && i < capacity && ss; ++i) {
+    const Section& s = plan->sections[static_cast<size_t>(i)];
+    double* o = ss + 9 * i;
+    o[0] = s.a[0]; o[1] = s.a[1]; o[2] = s.a[2]; o[3] = s.a[3];
+    o[4] = s.b0; o[5] = s.b1; o[6] = s.c[0]; o[7] = s.c[1]; o[8] = s.d;
+  }
+  return DSPB200_OK;
+}
+
+int dspb200_eq_run_f32(const dspb200_eq_plan* plan, const float* x, int64_t xs, float* z, int64_t zs,
+                       int64_t channels, int64_t n, void* stream) {
+  return eq_run<float>(plan, x, xs, z, zs, channels, n, static_cast<cudaStream_t>(stream));
+}
+int dspb200_eq_run_f64(const dspb200_eq_plan* plan, const double* x, int64_t xs, double* z, int64_t zs,
+                       int64_t channels, int64_t n, void* stream) {
+  return eq_run<double>(plan, x, xs, z, zs, channels, n, static_cast<cudaStream_t>(stream));
+}
+int dspb200_eq_host_f32(const dspb200_eq_plan* plan, const float* x, float* z, int64_t channels, int64_t n) {
+  DSP_CHECK(plan && plan->dtype == DSPB200_F32, "plan is NULL or not float32");
+  return eq_host<float>(plan, x, z, channels, n);
+}
+int dspb200_eq_host_f64(const dspb200_eq_plan* plan, const double* x, double* z, int64_t channels, int64_t n) {
+  DSP_CHECK(plan && plan->dtype == DSPB200_F64, "plan is NULL or not float64");
+  return eq_host<double>(plan, x, z, channels, n);
+}
+
+}  // extern "C"

@@ -1,0 +1,723 @@
+// K3 -- batched radix-2 FFT and windowed magnitude spectrum.
+//
+// Replaces fft_diezmado_en_tiempo (dsp_core.py:41-66) and the arithmetic of
+// calcular_espectro_magnitud (dsp_core.py:85-98: symmetric Hann, FFT, abs,
+// first N/2+1 bins).  The reference recurses a radix-2 decimation-in-time split
+// down to length 1; here the same radix-2 butterflies are grouped 4 levels at a
+// time into register-resident 16-point blocks (radix 2/4/8 for the remainder)
+// and the levels are chained Stockham-style through shared memory, so the
+// result is the same DFT in natural order without a bit-reversal pass.
+//
+// Real input uses the conjugate-symmetry trick: N real samples are read as N/2
+// complex points z[j] = x[2j] + i x[2j+1] (one 8/16-byte load per point, Hann
+// applied on the fly), transformed with an N/2-point complex FFT and split
+//     Xe = (Z[k] + conj Z[n-k]) / 2,  Xo = -i (Z[k] - conj Z[n-k]) / 2,
+//     |X[k]| = |Xe + W_N^k Xo|,  |X[n-k]| = |Xe - W_N^k Xo|,   n = N/2,
+// so only N/2+1 magnitudes are ever written.
+//
+// One CTA transforms one frame entirely on chip when n <= kSubMax (the 2048- and
+// 4096-point sizes of the app and of config C5).  Larger transforms (2^16 of
+// config C4) use a top-level radix-R decimation-in-time split: R interleaved
+// sub-sequences are transformed by R CTAs into a workspace (sized to stay
+// L2-resident) and a second kernel does the last radix-R level fused with the
+// real split and the magnitude.
+//
+// Twiddles are float64-accurate tables rounded to the working type (the
+// reference evaluates np.exp per level, dsp_core.py:59-60), never recurrences.
+//
+// Roofline (per frame of N real samples): N*sizeof(T) bytes read +
+// (N/2+1)*sizeof(T) written; ~2.5 N log2 N flop.
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace dspb200 {
+
+template <typename T> struct Cpx;
+template <> struct Cpx<float> { typedef float2 type; };
+template <> struct Cpx<double> { typedef double2 type; };
+
+template <typename T> struct FftCfg;
+template <> struct FftCfg<float> { static constexpr int kSubMax = 8192; };
+template <> struct FftCfg<double> { static constexpr int kSubMax = 4096; };
+
+constexpr int kPadShift = 4;  // one pad element per 16: conflict-free strided stores
+__host__ __device__ __forceinline__ int padded(int i) { return i + (i >> kPadShift); }
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+  C r;
+  r.x = a.x * b.x - a.y * b.y;
+  r.y = a.x * b.y + a.y * b.x;
+  return r;
+}
+template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
+template <typename C> __device__ __forceinline__ C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
+
+// cos/sin(2 pi k / 16), k = 0..7
+__device__ constexpr double kCos16[8] = {1.0, 0.92387953251128673848, 0.70710678118654752440,
+                                         0.38268343236508977173, 0.0, -0.38268343236508977173,
+                                         -0.70710678118654752440, -0.92387953251128673848};
+__device__ constexpr double kSin16[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440,
+                                         0.92387953251128673848, 1.0, 0.92387953251128673848,
+                                         0.70710678118654752440, 0.38268343236508977173};
+
+// R-point DFT in registers, natural order in and out: the reference's radix-2
+// decimation-in-time recursion (even/odd split, twiddle, butterfly) unrolled.
+template <typename T, int R> struct Dft {
+  typedef typename Cpx<T>::type C;
+  static __device__ __forceinline__ void run(C* v) {
+    C e[R / 2], o[R / 2];
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+    Dft<T, R / 2>::run(e);
+    Dft<T, R / 2>::run(o);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      C t;
+      if (k == 0) {
+        t = o[k];
+      } else if (4 * k == R) {
+        t = mul_neg_i(o[k]);
+      } else {
+        C w;
+        w.x = static_cast<T>(kCos16[k * (16 / R)]);
+        w.y = static_cast<T>(-kSin16[k * (16 / R)]);
+        t = cmul(w, o[k]);
+      }
+      v[k] = cadd(e[k], t);
+      v[k + R / 2] = csub(e[k], t);
+    }
+  }
+};
+template <typename T> struct Dft<T, 1> {
+  typedef typename Cpx<T>::type C;
+  static __device__ __forceinline__ void run(C*) {}
+};
+
+template <typename T> struct FftArgs {
+  typedef typename Cpx<T>::type C;
+  // input
+  const T* x;              // real frames: [channels, time]; c2c: interleaved complex
+  long long x_stride;
+  long long n_valid, offset, hop, n_frames;
+  const T* window;         // Hann [2*nc] or nullptr
+  // geometry
+  int nc;                  // complex points of the whole transform
+  int m;                   // complex points of the per-CTA sub-transform (nc = m * r_top)
+  int r_top;
+  int n_pass;
+  int radix[8];
+  const C* tw_sub;         // W_m[k]
+  const C* tw_top;         // W_nc[k]
+  const C* tw_post;        // W_(2nc)[k], k = 0..nc/2
+  // output
+  T* mag; long long mag_frame_stride, mag_channel_stride;
+  C* out;                  // c2c result or workspace
+  long long n_items;       // transforms * r_top
+};
+
+template <typename T, int R>
+__device__ __forceinline__ void load_pass(typename Cpx<T>::type* v, const typename Cpx<T>::type* s,
+                                          int t, int m) {
+  // thread t holds 16 points: B = 16/R butterflies of radix R
+  constexpr int B = 16 / R;
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    const int j = t + b * (m / 16);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[b * R + r] = s[padded(j + r * (m / R))];
+  }
+}
+
+template <typename T, int R, typename F>
+__device__ __forceinline__ void load_first(typename Cpx<T>::type* v, F& fetch, int t, int m) {
+  constexpr int B = 16 / R;
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    const int j = t + b * (m / 16);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[b * R + r] = fetch(j + r * (m / R));
+  }
+}
+
+template <typename T, int R>
+__device__ __forceinline__ void compute_store_pass(typename Cpx<T>::type* v, typename Cpx<T>::type* s,
+                                                   const typename Cpx<T>::type* __restrict__ tw, int t,
+                                                   int m, int ns) {
+  typedef typename Cpx<T>::type C;
+  constexpr int B = 16 / R;
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    const int j = t + b * (m / 16);
+    const int k = j & (ns - 1);
+    C* w = v + b * R;
+    if (ns > 1) {
+      const int stride = m / (ns * R);
+#pragma unroll
+      for (int r = 1; r < R; ++r) w[r] = cmul(w[r], tw[r * k * stride]);
+    }
+    Dft<T, R>::run(w);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[padded(base + r * ns)] = w[r];
+  }
+}
+
+// MODE 0: real frames -> magnitudes (r_top == 1)      MODE 1: real frames -> workspace
+// MODE 2: complex -> complex (r_top == 1)              MODE 3: complex -> workspace
+template <typename T, int MODE>
+__global__ void __launch_bounds__(512)
+fft_stockham_kernel(const FftArgs<T> a) {
+  typedef typename Cpx<T>::type C;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  const int t = threadIdx.x;
+  const int m = a.m;
+  const int nthr = m / 16;   // active threads
+  const bool active = t < nthr;
+  constexpr bool kReal = (MODE == 0 || MODE == 1);
+
+  for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const long long f = item / a.r_top;
+    const int rho = static_cast<int>(item - f * a.r_top);
+    C v[16];
+    // ---- first pass: operands come straight from global memory -------------
+    const int R0 = a.radix[0];
+    const T* xrow = nullptr;
+    long long fstart = 0;
+    bool fast = false;
+    if constexpr (kReal) {
+      const long long c = f / a.n_frames;
+      const long long fr = f - c * a.n_frames;
+      xrow = a.x + c * a.x_stride;
+      fstart = a.offset + fr * a.hop;
+      fast = (fstart + 2LL * a.nc <= a.n_valid) && (((reinterpret_cast<uintptr_t>(xrow + fstart)) % (2 * sizeof(T))) == 0);
+    }
+    auto fetch = [&](int j) -> C {   // element j of sub-sequence rho
+      const long long i = static_cast<long long>(a.r_top) * j + rho;
+      C z;
+      if constexpr (kReal) {
+        if (fast) {
+          z = *reinterpret_cast<const C*>(xrow + fstart + 2 * i);
+        } else {
+          const long long s0 = fstart + 2 * i;
+          z.x = s0 < a.n_valid ? xrow[s0] : T(0);
+          z.y = s0 + 1 < a.n_valid ? xrow[s0 + 1] : T(0);
+        }
+        if (a.window) {
+          const C w = *reinterpret_cast<const C*>(a.window + 2 * i);
+          z.x *= w.x;
+          z.y *= w.y;
+        }
+      } else {
+        z = reinterpret_cast<const C*>(a.x)[f * a.nc + i];
+      }
+      return z;
+    };
+    if (active) {
+      switch (R0) {
+        case 16: load_first<T, 16>(v, fetch, t, m); break;
+        case 8: load_first<T, 8>(v, fetch, t, m); break;
+        case 4: load_first<T, 4>(v, fetch, t, m); break;
+        default: load_first<T, 2>(v, fetch, t, m); break;
+      }
+    }
+    __syncthreads();   // previous item's readers are done with s
+    int ns = 1;
+    for (int pass = 0; pass < a.n_pass; ++pass) {
+      const int R = a.radix[pass];
+      if (pass > 0) {
+        if (active) {
+          switch (R) {
+            case 16: load_pass<T, 16>(v, s, t, m); break;
+            case 8: load_pass<T, 8>(v, s, t, m); break;
+            case 4: load_pass<T, 4>(v, s, t, m); break;
+            default: load_pass<T, 2>(v, s, t, m); break;
+          }
+        }
+        __syncthreads();
+      }
+      if (active) {
+        switch (R) {
+          case 16: compute_store_pass<T, 16>(v, s, a.tw_sub, t, m, ns); break;
+          case 8: compute_store_pass<T, 8>(v, s, a.tw_sub, t, m, ns); break;
+          case 4: compute_store_pass<T, 4>(v, s, a.tw_sub, t, m, ns); break;
+          default: compute_store_pass<T, 2>(v, s, a.tw_sub, t, m, ns); break;
+        }
+      }
+      __syncthreads();
+      ns *= R;
+    }
+    // ---- epilogue ----------------------------------------------------------
+    if constexpr (MODE == 0) {
+      const long long c = f / a.n_frames;
+      const long long fr = f - c * a.n_frames;
+      T* mg = a.mag + c * a.mag_channel_stride + fr * a.mag_frame_stride;
+      const int nc = a.nc;
+      for (int k = t; k <= nc / 2; k += blockDim.x) {
+        const C A = s[padded(k)];
+        const C Bc = cconj(s[padded((nc - k) & (nc - 1))]);
+        C xe, xo;
+        xe.x = T(0.5) * (A.x + Bc.x); xe.y = T(0.5) * (A.y + Bc.y);
+        // -i/2 * (A - B)
+        xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
+        const C tt = cmul(a.tw_post[k], xo);
+        const C p = cadd(xe, tt), q = csub(xe, tt);
+        mg[k] = sqrt(p.x * p.x + p.y * p.y);
+        mg[nc - k] = sqrt(q.x * q.x + q.y * q.y);
+      }
+    } else if constexpr (MODE == 2) {
+      C* o = a.out + f * a.nc;
+      for (int k = t; k < m; k += blockDim.x) o[k] = s[padded(k)];
+    } else {
+      C* o = a.out + item * m;
+      for (int k = t; k < m; k += blockDim.x) o[k] = s[padded(k)];
+    }
+    // the __syncthreads at the top of the next item protects s
+  }
+}
+
+// Last radix-R level of a split transform, fused with the real split + |.|
+// (kReal) or writing the complex result.  ws: [transform][rho][m].
+template <typename T, int R, bool kReal>
+__global__ void __launch_bounds__(256)
+fft_combine_kernel(const FftArgs<T> a, const typename Cpx<T>::type* __restrict__ ws, long long n_transforms) {
+  typedef typename Cpx<T>::type C;
+  const int m = a.m, nc = a.nc;
+  const int per = kReal ? (m / 2 + 1) : m;
+  const long long total = n_transforms * per;
+  for (long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; id < total;
+       id += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = id / per;
+    const int k = static_cast<int>(id - f * per);
+    const C* w = ws + f * nc;
+    C za[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      za[r] = w[static_cast<long long>(r) * m + k];
+      if (r > 0) za[r] = cmul(za[r], a.tw_top[r * k]);
+    }
+    Dft<T, R>::run(za);
+    if constexpr (!kReal) {
+      C* o = a.out + f * nc;
+#pragma unroll
+      for (int s = 0; s < R; ++s) o[k + s * m] = za[s];
+    } else {
+      const int k2 = (m - k) & (m - 1);
+      C zb[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        zb[r] = w[static_cast<long long>(r) * m + k2];
+        if (r > 0) zb[r] = cmul(zb[r], a.tw_top[r * k2]);
+      }
+      Dft<T, R>::run(zb);
+      const long long c = f / a.n_frames;
+      const long long fr = f - c * a.n_frames;
+      T* mg = a.mag + c * a.mag_channel_stride + fr * a.mag_frame_stride;
+      auto emit = [&](const C A, const C Bz, int idx) {
+        if (idx > nc / 2) return;
+        const C Bc = cconj(Bz);
+        C xe, xo;
+        xe.x = T(0.5) * (A.x + Bc.x); xe.y = T(0.5) * (A.y + Bc.y);
+        xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
+        const C tt = cmul(a.tw_post[idx], xo);
+        const C p = cadd(xe, tt), q = csub(xe, tt);
+        mg[idx] = sqrt(p.x * p.x + p.y * p.y);
+        mg[nc - idx] = sqrt(q.x * q.x + q.y * q.y);
+      };
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const int sp = (k == 0) ? ((R - s) & (R - 1)) : (R - 1 - s);
+        emit(za[s], zb[sp], k + s * m);
+        if (k != 0 && k != k2) emit(zb[s], za[sp], k2 + s * m);
+      }
+    }
+  }
+}
+
+// Direct DFT for tiny transforms (nc < 16): one thread per output bin.
+template <typename T, bool kReal>
+__global__ void __launch_bounds__(128)
+fft_small_kernel(const FftArgs<T> a, const typename Cpx<T>::type* __restrict__ tw_full, int n_fft,
+                 long long n_transforms) {
+  typedef typename Cpx<T>::type C;
+  const int per = kReal ? (n_fft / 2 + 1) : n_fft;
+  const long long total = n_transforms * per;
+  for (long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; id < total;
+       id += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = id / per;
+    const int k = static_cast<int>(id - f * per);
+    C acc; acc.x = T(0); acc.y = T(0);
+    if constexpr (kReal) {
+      const long long c = f / a.n_frames;
+      const long long fr = f - c * a.n_frames;
+      const T* xrow = a.x + c * a.x_stride;
+      const long long fstart = a.offset + fr * a.hop;
+      for (int t = 0; t < n_fft; ++t) {
+        T xv = fstart + t < a.n_valid ? xrow[fstart + t] : T(0);
+        if (a.window) xv *= a.window[t];
+        const C w = tw_full[(t * k) & (n_fft - 1)];
+        acc.x += xv * w.x;
+        acc.y += xv * w.y;
+      }
+      a.mag[c * a.mag_channel_stride + fr * a.mag_frame_stride + k] = sqrt(acc.x * acc.x + acc.y * acc.y);
+    } else {
+      const C* in = reinterpret_cast<const C*>(a.x) + f * n_fft;
+      for (int t = 0; t < n_fft; ++t) acc = cadd(acc, cmul(in[t], tw_full[(t * k) & (n_fft - 1)]));
+      a.out[f * n_fft + k] = acc;
+    }
+  }
+}
+
+struct FftSide {
+  int nc = 0, m = 0, r_top = 1, n_pass = 0;
+  int radix[8] = {0};
+  void* d_tw_sub = nullptr;
+  void* d_tw_top = nullptr;
+  void* d_tw_post = nullptr;
+};
+
+}  // namespace dspb200
+
+struct dspb200_fft_plan {
+  int n_fft, hann, dtype, device;
+  dspb200::FftSide real_side, c2c_side;
+  void* d_window = nullptr;
+  void* d_tw_full = nullptr;   // W_N, for the direct small-size kernel
+};
+
+namespace dspb200 {
+
+static const long double kPiL = 3.14159265358979323846264338327950288L;
+
+template <typename T>
+static int upload_twiddles(int n, int count, void** dptr) {   // W_n[k], k = 0..count-1
+  typedef typename Cpx<T>::type C;
+  *dptr = nullptr;
+  if (count <= 0) return DSPB200_OK;
+  std::vector<C> h(static_cast<size_t>(count));
+  for (int k = 0; k < count; ++k) {
+    // exact octant reduction keeps every entry correctly rounded
+    const long double ang = -2.0L * kPiL * static_cast<long double>(k) / static_cast<long double>(n);
+    h[static_cast<size_t>(k)].x = static_cast<T>(cosl(ang));
+    h[static_cast<size_t>(k)].y = static_cast<T>(sinl(ang));
+  }
+  DSP_CUDA(cudaMalloc(dptr, h.size() * sizeof(C)));
+  DSP_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(C), cudaMemcpyHostToDevice));
+  return DSPB200_OK;
+}
+
+template <typename T>
+static int build_side(FftSide& s, int nc, bool real) {
+  s.nc = nc;
+  if (nc < 16) return DSPB200_OK;   // served by the direct kernel
+  const int sub_max = FftCfg<T>::kSubMax;
+  s.m = nc <= sub_max ? nc : sub_max;
+  s.r_top = nc / s.m;
+  if (s.r_top > 16) return fail(DSPB200_ERR_UNSUPPORTED, "transform too long (complex length %d)", nc);
+  int rest = s.m, n16 = 0;
+  while (rest % 16 == 0 && rest > 1) { rest /= 16; ++n16; }
+  s.n_pass = 0;
+  if (rest > 1) s.radix[s.n_pass++] = rest;
+  for (int i = 0; i < n16; ++i) s.radix[s.n_pass++] = 16;
+  DSP_TRY(upload_twiddles<T>(s.m, s.m, &s.d_tw_sub));
+  if (s.r_top > 1) DSP_TRY(upload_twiddles<T>(nc, nc, &s.d_tw_top));
+  if (real) DSP_TRY(upload_twiddles<T>(2 * nc, nc / 2 + 1, &s.d_tw_post));
+  return DSPB200_OK;
+}
+
+template <typename T>
+static int plan_build(dspb200_fft_plan* p) {
+  const int N = p->n_fft;
+  DSP_TRY(build_side<T>(p->real_side, N / 2, true));
+  {
+    // a complex side that is too long only disables the complex entry points
+    const int rc = build_side<T>(p->c2c_side, N, false);
+    if (rc == DSPB200_ERR_UNSUPPORTED) p->c2c_side.nc = -1;
+    else if (rc != DSPB200_OK) return rc;
+  }
+  if (N < 32) DSP_TRY(upload_twiddles<T>(N, N, &p->d_tw_full));
+  if (p->hann) {
+    std::vector<T> w(static_cast<size_t>(N));
+    for (int k = 0; k < N; ++k) {
+      // 0.5 - 0.5 cos(2 pi k / (N-1)); N == 1 gives 0/0 = NaN as in dsp_core.py:87
+      const double ratio = static_cast<double>(k) / static_cast<double>(N - 1);
+      w[static_cast<size_t>(k)] = static_cast<T>(0.5 - 0.5 * std::cos(2.0 * 3.14159265358979323846 * ratio));
+    }
+    DSP_CUDA(cudaMalloc(&p->d_window, w.size() * sizeof(T)));
+    DSP_CUDA(cudaMemcpy(p->d_window, w.data(), w.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  return DSPB200_OK;
+}
+
+static size_t side_workspace(const FftSide& s, int64_t n_transforms, size_t csize) {
+  if (s.nc < 16 || s.r_top == 1) return 0;
+  return static_cast<size_t>(n_transforms) * s.nc * csize;
+}
+
+template <typename T>
+static void fill_args(FftArgs<T>& a, const FftSide& s) {
+  typedef typename Cpx<T>::type C;
+  a.nc = s.nc; a.m = s.m; a.r_top = s.r_top; a.n_pass = s.n_pass;
+  for (int i = 0; i < 8; ++i) a.radix[i] = s.radix[i];
+  a.tw_sub = static_cast<const C*>(s.d_tw_sub);
+  a.tw_top = static_cast<const C*>(s.d_tw_top);
+  a.tw_post = static_cast<const C*>(s.d_tw_post);
+}
+
+template <typename T, int MODE>
+static int launch_stockham(const FftArgs<T>& a, cudaStream_t stream) {
+  typedef typename Cpx<T>::type C;
+  const size_t smem = static_cast<size_t>(padded(a.m) + 1) * sizeof(C);
+  auto kern = fft_stockham_kernel<T, MODE>;
+  DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int threads = a.m / 16;
+  if (threads < 32) threads = 32;
+  int per_sm = 1;
+  DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  const int grid = static_cast<int>(a.n_items < cap ? a.n_items : cap);
+  kern<<<grid, threads, smem, stream>>>(a);
+  return after_launch("fft_stockham_kernel");
+}
+
+template <typename T, bool kReal>
+static int launch_combine(const FftArgs<T>& a, const typename Cpx<T>::type* ws, long long n_tr, cudaStream_t stream) {
+  const int per = kReal ? (a.m / 2 + 1) : a.m;
+  const long long total = n_tr * per;
+  const int threads = 256;
+  long long blocks = ceil_div(total, threads);
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  switch (a.r_top) {
+    case 2: fft_combine_kernel<T, 2, kReal><<<static_cast<int>(blocks), threads, 0, stream>>>(a, ws, n_tr); break;
+    case 4: fft_combine_kernel<T, 4, kReal><<<static_cast<int>(blocks), threads, 0, stream>>>(a, ws, n_tr); break;
+    case 8: fft_combine_kernel<T, 8, kReal><<<static_cast<int>(blocks), threads, 0, stream>>>(a, ws, n_tr); break;
+    case 16: fft_combine_kernel<T, 16, kReal><<<static_cast<int>(blocks), threads, 0, stream>>>(a, ws, n_tr); break;
+    default: return fail(DSPB200_ERR_UNSUPPORTED, "internal: top radix %d", a.r_top);
+  }
+  return after_launch("fft_combine_kernel");
+}
+
+template <typename T>
+int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_valid, int64_t offset, int64_t hop,
+               int64_t n_frames, T* mag, int64_t mfs, int64_t mcs, int64_t channels, void* ws, size_t ws_bytes,
+               cudaStream_t stream) {
+  typedef typename Cpx<T>::type C;
+  DSP_CHECK(p != nullptr, "plan is NULL");
+  DSP_CHECK(p->dtype == DType<T>::id, "plan dtype %d does not match the entry point", p->dtype);
+  DSP_CHECK(channels >= 0 && n_frames >= 0 && n_valid >= 0 && offset >= 0 && hop >= 0, "negative argument");
+  if (channels == 0 || n_frames == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr && mag != nullptr, "NULL buffer");
+  DSP_CHECK(mfs >= p->n_fft / 2 + 1, "mag_frame_stride smaller than n_fft/2+1");
+  DSP_TRY(ensure_device());
+  const int64_t n_tr = channels * n_frames;
+  FftArgs<T> a{};
+  a.x = x; a.x_stride = xs; a.n_valid = n_valid; a.offset = offset; a.hop = hop; a.n_frames = n_frames;
+  a.window = static_cast<const T*>(p->d_window);
+  a.mag = mag; a.mag_frame_stride = mfs; a.mag_channel_stride = mcs;
+  const FftSide& s = p->real_side;
+  if (p->n_fft < 32) {
+    const int per = p->n_fft / 2 + 1;
+    const int threads = 128;
+    long long blocks = ceil_div(n_tr * per, threads);
+    if (blocks > 65535) blocks = 65535;
+    fft_small_kernel<T, true><<<static_cast<int>(blocks), threads, 0, stream>>>(
+        a, static_cast<const C*>(p->d_tw_full), p->n_fft, n_tr);
+    return after_launch("fft_small_kernel");
+  }
+  fill_args(a, s);
+  a.n_items = n_tr * s.r_top;
+  if (s.r_top == 1) return launch_stockham<T, 0>(a, stream);
+  const size_t need = side_workspace(s, n_tr, sizeof(C));
+  DSP_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  a.out = static_cast<C*>(ws);
+  DSP_TRY((launch_stockham<T, 1>(a, stream)));
+  return launch_combine<T, true>(a, static_cast<const C*>(ws), n_tr, stream);
+}
+
+template <typename T>
+int fft_c2c_run(const dspb200_fft_plan* p, const T* in, T* out, int64_t batch, void* ws, size_t ws_bytes,
+                cudaStream_t stream) {
+  typedef typename Cpx<T>::type C;
+  DSP_CHECK(p != nullptr, "plan is NULL");
+  DSP_CHECK(p->dtype == DType<T>::id, "plan dtype %d does not match the entry point", p->dtype);
+  DSP_CHECK(batch >= 0, "negative batch");
+  if (batch == 0) return DSPB200_OK;
+  DSP_CHECK(in != nullptr && out != nullptr, "NULL buffer");
+  DSP_CHECK(in != out, "in-place complex transform is not supported");
+  DSP_TRY(ensure_device());
+  FftArgs<T> a{};
+  a.x = in; a.out = reinterpret_cast<C*>(out); a.n_frames = 1;
+  const FftSide& s = p->c2c_side;
+  if (p->n_fft < 16) {
+    const int threads = 128;
+    long long blocks = ceil_div(batch * p->n_fft, threads);
+    if (blocks > 65535) blocks = 65535;
+    fft_small_kernel<T, false><<<static_cast<int>(blocks), threads, 0, stream>>>(
+        a, static_cast<const C*>(p->d_tw_full), p->n_fft, batch);
+    return after_launch("fft_small_kernel");
+  }
+  fill_args(a, s);
+  a.n_items = batch * s.r_top;
+  if (s.r_top == 1) return launch_stockham<T, 2>(a, stream);
+  const size_t need = side_workspace(s, batch, sizeof(C));
+  DSP_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  C* final_out = a.out;
+  a.out = static_cast<C*>(ws);
+  DSP_TRY((launch_stockham<T, 3>(a, stream)));
+  a.out = final_out;
+  return launch_combine<T, false>(a, static_cast<const C*>(ws), batch, stream);
+}
+
+template int fftmag_run<float>(const dspb200_fft_plan*, const float*, int64_t, int64_t, int64_t, int64_t, int64_t, float*, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t);
+template int fftmag_run<double>(const dspb200_fft_plan*, const double*, int64_t, int64_t, int64_t, int64_t, int64_t, double*, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t);
+
+int fft_plan_info(const dspb200_fft_plan* plan, int* n_fft, int* dtype) {
+  if (!plan) return fail(DSPB200_ERR_INVALID, "fft plan is NULL");
+  *n_fft = plan->n_fft; *dtype = plan->dtype;
+  return DSPB200_OK;
+}
+
+template <typename T>
+static int fftmag_host(const dspb200_fft_plan* p, const T* x, int64_t channels, int64_t n_samples, int64_t offset,
+                       int64_t hop, int64_t n_frames, T* mag) {
+  typedef typename Cpx<T>::type C;
+  DSP_CHECK(p != nullptr, "plan is NULL");
+  DSP_CHECK(channels >= 0 && n_samples >= 0 && n_frames >= 0, "negative shape");
+  if (channels == 0 || n_frames == 0) return DSPB200_OK;
+  DSP_CHECK(mag != nullptr && (x != nullptr || n_samples == 0), "NULL buffer");
+  DSP_TRY(ensure_device());
+  const int bins = p->n_fft / 2 + 1;
+  const int64_t pitch = round_up(n_samples > 0 ? n_samples : 1, 16 / static_cast<int64_t>(sizeof(T)));
+  T *dx = nullptr, *dm = nullptr;
+  void* ws = nullptr;
+  const size_t need = side_workspace(p->real_side, channels * n_frames, sizeof(C));
+  cudaError_t e = cudaMalloc(&dx, static_cast<size_t>(channels) * pitch * sizeof(T));
+  if (e == cudaSuccess) e = cudaMalloc(&dm, static_cast<size_t>(channels) * n_frames * bins * sizeof(T));
+  if (e == cudaSuccess && need) e = cudaMalloc(&ws, need);
+  int rc = DSPB200_OK;
+  if (e == cudaSuccess && n_samples > 0)
+    e = cudaMemcpy2DAsync(dx, pitch * sizeof(T), x, n_samples * sizeof(T), n_samples * sizeof(T), channels,
+                          cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess)
+    rc = fftmag_run<T>(p, dx, pitch, n_samples, offset, hop, n_frames, dm, bins, n_frames * bins, channels, ws, need, nullptr);
+  if (e == cudaSuccess && rc == DSPB200_OK)
+    e = cudaMemcpyAsync(mag, dm, static_cast<size_t>(channels) * n_frames * bins * sizeof(T), cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(dx); cudaFree(dm); cudaFree(ws);
+  if (e != cudaSuccess) return fail(DSPB200_ERR_CUDA, "fftmag host path: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+}  // namespace dspb200
+
+using namespace dspb200;
+
+extern "C" {
+
+int dspb200_fft_plan_create(int n_fft, int hann, int dtype, dspb200_fft_plan** plan) {
+  DSP_CHECK(plan != nullptr, "plan output pointer is NULL");
+  DSP_CHECK(n_fft >= 1 && (n_fft & (n_fft - 1)) == 0, "n_fft must be a power of two (got %d)", n_fft);
+  DSP_CHECK(n_fft <= DSPB200_FFT_MAX, "n_fft above %d is not supported", DSPB200_FFT_MAX);
+  DSP_CHECK(dtype == DSPB200_F32 || dtype == DSPB200_F64, "dtype must be 0 (f32) or 1 (f64)");
+  DSP_TRY(ensure_device());
+  dspb200_fft_plan* p = new (std::nothrow) dspb200_fft_plan();
+  if (!p) return fail(DSPB200_ERR_ALLOC, "out of host memory");
+  p->n_fft = n_fft; p->hann = hann ? 1 : 0; p->dtype = dtype;
+  cudaGetDevice(&p->device);
+  int rc = dtype == DSPB200_F32 ? plan_build<float>(p) : plan_build<double>(p);
+  if (rc != DSPB200_OK) {
+    dspb200_fft_plan_destroy(p);
+    return rc;
+  }
+  *plan = p;
+  return DSPB200_OK;
+}
+
+int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
+  if (!p) return DSPB200_OK;
+  FftSide* sides[2] = {&p->real_side, &p->c2c_side};
+  for (FftSide* s : sides) {
+    cudaFree(s->d_tw_sub);
+    cudaFree(s->d_tw_top);
+    cudaFree(s->d_tw_post);
+  }
+  cudaFree(p->d_window);
+  cudaFree(p->d_tw_full);
+  delete p;
+  return DSPB200_OK;
+}
+
+int dspb200_fft_workspace_bytes(const dspb200_fft_plan* p, int64_t n_transforms, size_t* bytes) {
+  DSP_CHECK(p != nullptr && bytes != nullptr, "NULL argument");
+  DSP_CHECK(n_transforms >= 0, "negative transform count");
+  const size_t csize = p->dtype == DSPB200_F32 ? 8 : 16;
+  const size_t r = side_workspace(p->real_side, n_transforms, csize);
+  const size_t c = p->c2c_side.nc > 0 ? side_workspace(p->c2c_side, n_transforms, csize) : 0;
+  *bytes = r > c ? r : c;
+  return DSPB200_OK;
+}
+
+int dspb200_fftmag_run_f32(const dspb200_fft_plan* p, const float* x, int64_t xs, int64_t n_valid, int64_t offset,
+                           int64_t hop, int64_t n_frames, float* mag, int64_t mfs, int64_t mcs, int64_t channels,
+                           void* ws, size_t ws_bytes, void* stream) {
+  return fftmag_run<float>(p, x, xs, n_valid, offset, hop, n_frames, mag, mfs, mcs, channels, ws, ws_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+int dspb200_fftmag_run_f64(const dspb200_fft_plan* p, const double* x, int64_t xs, int64_t n_valid, int64_t offset,
+                           int64_t hop, int64_t n_frames, double* mag, int64_t mfs, int64_t mcs, int64_t channels,
+                           void* ws, size_t ws_bytes, void* stream) {
+  return fftmag_run<double>(p, x, xs, n_valid, offset, hop, n_frames, mag, mfs, mcs, channels, ws, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+int dspb200_fft_c2c_run_f32(const dspb200_fft_plan* p, const float* in, float* out, int64_t batch, void* ws,
+                            size_t ws_bytes, void* stream) {
+  DSP_CHECK(p && p->c2c_side.nc > 0, "plan is NULL or too long for the complex transform");
+  return fft_c2c_run<float>(p, in, out, batch, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int dspb200_fft_c2c_run_f64(const dspb200_fft_plan* p, const double* in, double* out, int64_t batch, void* ws,
+                            size_t ws_bytes, void* stream) {
+  DSP_CHECK(p && p->c2c_side.nc > 0, "plan is NULL or too long for the complex transform");
+  return fft_c2c_run<double>(p, in, out, batch, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int dspb200_fftmag_host_f32(const dspb200_fft_plan* p, const float* x, int64_t channels, int64_t n_samples,
+                            int64_t offset, int64_t hop, int64_t n_frames, float* mag) {
+  DSP_CHECK(p && p->dtype == DSPB200_F32, "plan is NULL or not float32");
+  return fftmag_host<float>(p, x, channels, n_samples, offset, hop, n_frames, mag);
+}
+int dspb200_fftmag_host_f64(const dspb200_fft_plan* p, const double* x, int64_t channels, int64_t n_samples,
+                            int64_t offset, int64_t hop, int64_t n_frames, double* mag) {
+  DSP_CHECK(p && p->dtype == DSPB200_F64, "plan is NULL or not float64");
+  return fftmag_host<double>(p, x, channels, n_samples, offset, hop, n_frames, mag);
+}
+int dspb200_fft_c2c_host_f64(const dspb200_fft_plan* p, const double* in, double* out, int64_t batch) {
+  DSP_CHECK(p && p->dtype == DSPB200_F64 && p->c2c_side.nc > 0, "plan is NULL, not float64 or too long");
+  DSP_CHECK(batch >= 0, "negative batch");
+  if (batch == 0) return DSPB200_OK;
+  DSP_CHECK(in != nullptr && out != nullptr, "NULL buffer");
+  DSP_TRY(ensure_device());
+  const size_t bytes = static_cast<size_t>(batch) * p->n_fft * 16;
+  const size_t need = side_workspace(p->c2c_side, batch, 16);
+  double *di = nullptr, *dout = nullptr;
+  void* ws = nullptr;
+  cudaError_t e = cudaMalloc(&di, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, bytes);
+  if (e == cudaSuccess && need) e = cudaMalloc(&ws, need);
+  int rc = DSPB200_OK;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(di, in, bytes, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) rc = fft_c2c_run<double>(p, di, dout, batch, ws, need, nullptr);
+  if (e == cudaSuccess && rc == DSPB200_OK) e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(di); cudaFree(dout); cudaFree(ws);
+  if (e != cudaSuccess) return fail(DSPB200_ERR_CUDA, "fft c2c host path: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+}  // extern "C"

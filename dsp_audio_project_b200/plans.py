@@ -1,0 +1,377 @@
+"""Plan objects over the C ABI: SRC, EQ and FFT.
+
+A plan owns device-side tables (polyphase tap rows, biquad state-space tables,
+twiddles/window) and is immutable after creation.  Two call styles:
+
+* ``run(...)`` -- batched ``[channels, time]`` torch CUDA tensors, enqueued on
+  torch's current stream (torch is only the allocator / stream provider);
+* ``run_host(...)`` -- numpy arrays in host memory; the library does the copies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+
+import numpy as np
+
+from . import _lib
+from ._lib import F32, F64, check
+
+BAND_CENTRES_HZ = {  # dsp_core.py:225-228
+    "Sub-Bass": 40, "Bass": 150, "Low Mids": 1000,
+    "High Mids": 3000, "Presence": 5000, "Brilliance": 10000,
+}
+BAND_ORDER = tuple(BAND_CENTRES_HZ)
+UNKNOWN_BAND_HZ = 1000  # dsp_core.py:235
+
+
+def _dtype_id(dtype) -> int:
+    name = str(dtype)
+    if name.startswith("torch."):
+        if name == "torch.float32":
+            return F32
+        if name == "torch.float64":
+            return F64
+        raise TypeError(f"unsupported dtype {dtype}; use float32 or float64")
+    dt = np.dtype(dtype)
+    if dt == np.float32:
+        return F32
+    if dt == np.float64:
+        return F64
+    raise TypeError(f"unsupported dtype {dt}; use float32 or float64")
+
+
+def _np_dtype(dtype_id: int):
+    return np.float32 if dtype_id == F32 else np.float64
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(t) -> int:
+    torch = _torch()
+    return int(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check_tensor(t, dtype_id, name):
+    torch = _torch()
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError(f"{name} must be a CUDA torch tensor (no CPU fallback)")
+    want = torch.float32 if dtype_id == F32 else torch.float64
+    if t.dtype != want:
+        raise TypeError(f"{name} has dtype {t.dtype}, plan wants {want}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name} must be [channels, time] with unit time stride")
+
+
+def _as_host(x, dtype_id, name="x"):
+    a = np.ascontiguousarray(x, dtype=_np_dtype(dtype_id))
+    if a.ndim == 1:
+        a = a[None, :]
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be [time] or [channels, time]")
+    return a
+
+
+def src_geometry(L: int, M: int, n_in: int):
+    """(taps, centre offset P, n_out) -- SURVEY.md 8a row a1 / dsp_core.py:155-170."""
+    t = C.c_int()
+    p = C.c_int64()
+    n = C.c_int64()
+    check(_lib.load().dspb200_src_geometry(int(L), int(M), int(n_in), C.byref(t), C.byref(p), C.byref(n)))
+    return t.value, p.value, n.value
+
+
+class SrcPlan:
+    """L/M polyphase resampler (replaces conversion_tasa_muestreo, dsp_core.py:133-173)."""
+
+    def __init__(self, L: int, M: int, dtype=np.float32):
+        self.L, self.M = int(L), int(M)
+        self.dtype_id = _dtype_id(dtype)
+        self._h = C.c_void_p()
+        check(_lib.load().dspb200_src_plan_create(self.L, self.M, self.dtype_id, C.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.load().dspb200_src_plan_destroy(h)
+
+    def out_len(self, n_in: int) -> int:
+        return src_geometry(self.L, self.M, n_in)[2]
+
+    def kernel_kind(self, channels: int, n_in: int) -> str:
+        k = C.c_int()
+        check(_lib.load().dspb200_src_plan_kernel_kind(self._h, channels, n_in, n_in, C.byref(k)))
+        return "tiled" if k.value == 1 else "generic"
+
+    def run(self, x, out=None, *, force_generic=False):
+        torch = _torch()
+        _check_tensor(x, self.dtype_id, "x")
+        ch, n_in = x.shape
+        n_out = self.out_len(n_in)
+        if out is None:
+            pitch = -(-n_out // 4) * 4          # keep rows 16-byte aligned for vector stores
+            out = torch.empty((ch, pitch), dtype=x.dtype, device=x.device)[:, :n_out]
+        _check_tensor(out, self.dtype_id, "out")
+        if out.shape != (ch, n_out):
+            raise ValueError(f"out must be [{ch}, {n_out}]")
+        lib = _lib.load()
+        suffix = "f32" if self.dtype_id == F32 else "f64"
+        fn = getattr(lib, ("dspb200_src_run_generic_" if force_generic else "dspb200_src_run_") + suffix)
+        with torch.cuda.device(x.device):
+            check(fn(self._h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n_in,
+                     _stream_ptr(x)))
+        return out
+
+    def run_host(self, x):
+        a = _as_host(x, self.dtype_id)
+        ch, n_in = a.shape
+        n_out = self.out_len(n_in)
+        y = np.empty((ch, n_out), dtype=a.dtype)
+        got = C.c_int64()
+        fn = _lib.load().dspb200_src_host_f32 if self.dtype_id == F32 else _lib.load().dspb200_src_host_f64
+        check(fn(self.L, self.M, a.ctypes.data, ch, n_in, y.ctypes.data, n_out, C.byref(got)))
+        return y
+
+
+def select_sections(fs: float, gains: dict):
+    """The cascade's band rules (dsp_core.py:222-251) in the caller's dict
+    order.  Returns (bypass, [(fc_eff, gain_db), ...])."""
+    names = list(gains.keys())
+    n = len(names)
+    fc = (C.c_double * max(n, 1))(*[float(BAND_CENTRES_HZ.get(k, UNKNOWN_BAND_HZ)) for k in names])
+    g = (C.c_double * max(n, 1))(*[float(gains[k]) for k in names])
+    fce = (C.c_double * max(n, 1))()
+    ge = (C.c_double * max(n, 1))()
+    na = C.c_int()
+    byp = C.c_int()
+    check(_lib.load().dspb200_eq_select_sections(float(fs), fc, g, n, fce, ge, C.byref(na), C.byref(byp)))
+    return bool(byp.value), [(fce[i], ge[i]) for i in range(na.value)]
+
+
+class EqPlan:
+    """Biquad cascade (replaces sistema_ecualizador / aplicar_ecuacion_diferencias,
+    dsp_core.py:205-254).  ``sections`` = [(fc_eff, gain_db), ...]."""
+
+    def __init__(self, fs: float, sections, dtype=np.float32, clip: bool = True, raw_ba=None):
+        self.dtype_id = _dtype_id(dtype)
+        self._h = C.c_void_p()
+        lib = _lib.load()
+        if raw_ba is not None:
+            ba = np.ascontiguousarray(raw_ba, dtype=np.float64).reshape(-1, 6)
+            self.n_sections = ba.shape[0]
+            check(lib.dspb200_eq_plan_create_raw(ba.ctypes.data_as(C.POINTER(C.c_double)), self.n_sections,
+                                                 int(bool(clip)), self.dtype_id, C.byref(self._h)))
+        else:
+            sections = list(sections)
+            self.n_sections = len(sections)
+            n = max(self.n_sections, 1)
+            fc = (C.c_double * n)(*[float(s[0]) for s in sections])
+            g = (C.c_double * n)(*[float(s[1]) for s in sections])
+            check(lib.dspb200_eq_plan_create(float(fs), fc, g, self.n_sections, int(bool(clip)),
+                                             self.dtype_id, C.byref(self._h)))
+
+    @classmethod
+    def from_gains(cls, fs: float, gains: dict, dtype=np.float32):
+        """Plan for a gains dict under the reference's rules; None when the
+        reference would bypass (return its input object untouched)."""
+        bypass, sections = select_sections(fs, gains)
+        if bypass:
+            return None
+        return cls(fs, sections, dtype=dtype, clip=True)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.load().dspb200_eq_plan_destroy(h)
+
+    def describe(self) -> np.ndarray:
+        n = C.c_int()
+        buf = np.zeros((16, 9))
+        check(_lib.load().dspb200_eq_plan_describe(self._h, C.byref(n), buf.ctypes.data_as(C.POINTER(C.c_double)), 16))
+        return buf[:n.value]
+
+    def run(self, x, out=None):
+        torch = _torch()
+        _check_tensor(x, self.dtype_id, "x")
+        if out is None:
+            out = torch.empty_like(x)
+        _check_tensor(out, self.dtype_id, "out")
+        if out.shape != x.shape:
+            raise ValueError("out must have x's shape")
+        ch, n = x.shape
+        fn = _lib.load().dspb200_eq_run_f32 if self.dtype_id == F32 else _lib.load().dspb200_eq_run_f64
+        with torch.cuda.device(x.device):
+            check(fn(self._h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, _stream_ptr(x)))
+        return out
+
+    def run_host(self, x):
+        a = _as_host(x, self.dtype_id)
+        z = np.empty_like(a)
+        fn = _lib.load().dspb200_eq_host_f32 if self.dtype_id == F32 else _lib.load().dspb200_eq_host_f64
+        check(fn(self._h, a.ctypes.data, z.ctypes.data, a.shape[0], a.shape[1]))
+        return z
+
+
+class FftPlan:
+    """Radix-2 FFT / Hann magnitude spectrum (replaces fft_diezmado_en_tiempo and
+    calcular_espectro_magnitud's arithmetic, dsp_core.py:41-98)."""
+
+    def __init__(self, n_fft: int, dtype=np.float32, hann: bool = True):
+        self.n_fft = int(n_fft)
+        self.bins = self.n_fft // 2 + 1
+        self.dtype_id = _dtype_id(dtype)
+        self._h = C.c_void_p()
+        check(_lib.load().dspb200_fft_plan_create(self.n_fft, int(bool(hann)), self.dtype_id, C.byref(self._h)))
+        self._ws = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.load().dspb200_fft_plan_destroy(h)
+
+    def workspace_bytes(self, n_transforms: int) -> int:
+        b = C.c_size_t()
+        check(_lib.load().dspb200_fft_workspace_bytes(self._h, int(n_transforms), C.byref(b)))
+        return int(b.value)
+
+    def _workspace(self, n_transforms, device):
+        torch = _torch()
+        need = self.workspace_bytes(n_transforms)
+        if need == 0:
+            return 0, 0
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws.data_ptr(), need
+
+    def n_frames(self, n: int, hop=None, offset: int = 0) -> int:
+        hop = self.n_fft if hop is None else int(hop)
+        return 0 if n - offset < self.n_fft else (n - offset - self.n_fft) // hop + 1
+
+    def magnitudes(self, x, *, hop=None, offset: int = 0, n_frames=None, n_valid=None, out=None):
+        """|FFT(hann * frame)|[:n_fft/2+1] for frames of x [channels, time] ->
+        [channels, n_frames, bins].  Samples at or beyond n_valid read as zero."""
+        torch = _torch()
+        _check_tensor(x, self.dtype_id, "x")
+        ch, n = x.shape
+        hop = self.n_fft if hop is None else int(hop)
+        n_valid = n if n_valid is None else int(n_valid)
+        if n_frames is None:
+            n_frames = self.n_frames(n, hop, offset)
+        if out is None:
+            out = torch.empty((ch, n_frames, self.bins), dtype=x.dtype, device=x.device)
+        if tuple(out.shape) != (ch, n_frames, self.bins) or not out.is_contiguous():
+            raise ValueError(f"out must be contiguous [{ch}, {n_frames}, {self.bins}]")
+        ws, ws_bytes = self._workspace(ch * n_frames, x.device)
+        fn = _lib.load().dspb200_fftmag_run_f32 if self.dtype_id == F32 else _lib.load().dspb200_fftmag_run_f64
+        with torch.cuda.device(x.device):
+            check(fn(self._h, x.data_ptr(), x.stride(0), n_valid, int(offset), hop, n_frames, out.data_ptr(),
+                     self.bins, n_frames * self.bins, ch, ws, ws_bytes, _stream_ptr(x)))
+        return out
+
+    def magnitudes_host(self, x, *, hop=None, offset: int = 0, n_frames=None):
+        a = _as_host(x, self.dtype_id)
+        ch, n = a.shape
+        hop = self.n_fft if hop is None else int(hop)
+        if n_frames is None:
+            n_frames = self.n_frames(n, hop, offset)
+        mag = np.empty((ch, n_frames, self.bins), dtype=a.dtype)
+        fn = _lib.load().dspb200_fftmag_host_f32 if self.dtype_id == F32 else _lib.load().dspb200_fftmag_host_f64
+        check(fn(self._h, a.ctypes.data if a.size else None, ch, n, int(offset), hop, n_frames, mag.ctypes.data))
+        return mag
+
+    def c2c(self, x, out=None):
+        """Complex transform of [batch, n_fft] complex tensors (natural order)."""
+        torch = _torch()
+        want = torch.complex64 if self.dtype_id == F32 else torch.complex128
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == want and x.is_contiguous()):
+            raise TypeError(f"x must be a contiguous CUDA {want} tensor")
+        if x.shape[-1] != self.n_fft:
+            raise ValueError("last dimension must equal n_fft")
+        batch = x.numel() // self.n_fft
+        if out is None:
+            out = torch.empty_like(x)
+        ws, ws_bytes = self._workspace(batch, x.device)
+        fn = _lib.load().dspb200_fft_c2c_run_f32 if self.dtype_id == F32 else _lib.load().dspb200_fft_c2c_run_f64
+        with torch.cuda.device(x.device):
+            check(fn(self._h, x.data_ptr(), out.data_ptr(), batch, ws, ws_bytes, _stream_ptr(x)))
+        return out
+
+    def c2c_host_f64(self, x):
+        a = np.ascontiguousarray(x, dtype=np.complex128)
+        if a.shape[-1] != self.n_fft:
+            raise ValueError("last dimension must equal n_fft")
+        if self.dtype_id != F64:
+            raise TypeError("c2c_host_f64 needs a float64 plan")
+        out = np.empty_like(a)
+        check(_lib.load().dspb200_fft_c2c_host_f64(self._h, a.ctypes.data, out.ctypes.data, a.size // self.n_fft))
+        return out
+
+
+class Chain:
+    """SRC -> EQ -> framed magnitude spectra (app.py:161-167, :202-205)."""
+
+    def __init__(self, L: int, M: int, fs_in: float, gains: dict, n_fft: int = 4096, dtype=np.float32):
+        self.dtype_id = _dtype_id(dtype)
+        self.L, self.M = int(L), int(M)
+        self.src = None if (self.L == 1 and self.M == 1) else SrcPlan(L, M, dtype)
+        self.fs_out = int(fs_in * self.L / self.M)  # dsp_core.py:172
+        self.eq = EqPlan.from_gains(self.fs_out, gains, dtype)
+        self.fft = FftPlan(n_fft, dtype, hann=True)
+        self._ws = None
+
+    def out_len(self, n_in):
+        return self.src.out_len(n_in) if self.src else n_in
+
+    def run(self, x, *, keep_y=False):
+        """x [channels, n_in] CUDA tensor -> (y or None, z, mag)."""
+        torch = _torch()
+        _check_tensor(x, self.dtype_id, "x")
+        ch, n_in = x.shape
+        n_out = self.out_len(n_in)
+        n_frames = n_out // self.fft.n_fft
+        z = torch.empty((ch, n_out), dtype=x.dtype, device=x.device)
+        y = torch.empty((ch, n_out), dtype=x.dtype, device=x.device) if (keep_y and self.src) else None
+        mag = torch.empty((ch, n_frames, self.fft.bins), dtype=x.dtype, device=x.device)
+        need = C.c_size_t()
+        lib = _lib.load()
+        check(lib.dspb200_chain_workspace_bytes(self.src._h if self.src else None, self.fft._h, ch, n_in,
+                                                int(keep_y), C.byref(need)))
+        if need.value and (self._ws is None or self._ws.numel() < need.value or self._ws.device != x.device):
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+        fn = lib.dspb200_chain_run_f32 if self.dtype_id == F32 else lib.dspb200_chain_run_f64
+        with torch.cuda.device(x.device):
+            check(fn(self.src._h if self.src else None, self.eq._h if self.eq else None, self.fft._h,
+                     x.data_ptr(), x.stride(0), ch, n_in, y.data_ptr() if y is not None else None,
+                     z.data_ptr(), mag.data_ptr(), self._ws.data_ptr() if need.value else None,
+                     need.value, _stream_ptr(x)))
+        return y, z, mag
+
+    def run_host(self, x, z=None, mag=None):
+        """Host numpy (ideally pinned) in, host arrays out; copies pipelined in slabs."""
+        a = x if (isinstance(x, np.ndarray) and x.flags.c_contiguous and x.dtype == _np_dtype(self.dtype_id)
+                  and x.ndim == 2) else _as_host(x, self.dtype_id)
+        ch, n_in = a.shape
+        n_out = self.out_len(n_in)
+        n_frames = n_out // self.fft.n_fft
+        if z is None:
+            z = np.empty((ch, n_out), dtype=a.dtype)
+        if mag is None:
+            mag = np.empty((ch, n_frames, self.fft.bins), dtype=a.dtype)
+        lib = _lib.load()
+        fn = lib.dspb200_chain_host_f32 if self.dtype_id == F32 else lib.dspb200_chain_host_f64
+        check(fn(self.src._h if self.src else None, self.eq._h if self.eq else None, self.fft._h,
+                 a.ctypes.data, ch, n_in, z.ctypes.data, mag.ctypes.data))
+        return z, mag
+
+
+@functools.lru_cache(maxsize=32)
+def cached_src_plan(L: int, M: int, dtype_id: int) -> SrcPlan:
+    return SrcPlan(L, M, _np_dtype(dtype_id))
+
+
+@functools.lru_cache(maxsize=32)
+def cached_fft_plan(n_fft: int, dtype_id: int, hann: bool) -> FftPlan:
+    return FftPlan(n_fft, _np_dtype(dtype_id), hann)

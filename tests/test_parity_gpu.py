@@ -1,0 +1,398 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+and the golden vectors generated from the real reference.
+
+Tolerances (north star): float64 kernels <= 1e-10 relative error
+(max|a-ref| / max|ref|); float32 fast path <= 1e-5 of full scale for SRC and
+FFT, <= 1e-4 of full scale for the EQ cascade.  Full scale is 1.0 for time
+signals and max|X| of the reference frame for spectra.
+"""
+import numpy as np
+import pytest
+
+from conftest import gains_dict
+from oracle import dsp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64 = 1e-10
+TOL_F32_SRC = 1e-5
+TOL_F32_FFT = 1e-5
+TOL_F32_EQ = 1e-4
+C1_GAINS = (6, -3, 4, -6, 3, -9)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("a CUDA device is required for -m gpu tests (no CPU fallback exists)")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import dsp_audio_project_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def dc():
+    from modules import dsp_core
+    return dsp_core
+
+
+# ------------------------------------------------------------------ SRC ----
+def test_src_golden_dropin(dc, golden_src):
+    g = golden_src
+    for idx, (L, M, N, fs_new, fs) in enumerate(g["cases"]):
+        x, y = g[f"x_{idx}"], g[f"y_{idx}"]
+        out, fs_out = dc.conversion_tasa_muestreo(x, int(fs), int(M), int(L))
+        assert fs_out == fs_new
+        if L == 1 and M == 1:
+            assert out is x
+            continue
+        assert out.dtype == np.float64 and out.shape == y.shape
+        assert o.rel_err(out, y) <= TOL_F64, (idx, L, M, N)
+
+
+def test_src_golden_f32_and_generic(pk, golden_src, torch_cuda):
+    torch = torch_cuda
+    g = golden_src
+    for idx, (L, M, N, fs_new, fs) in enumerate(g["cases"]):
+        if L == 1 and M == 1:
+            continue
+        x, y = g[f"x_{idx}"], g[f"y_{idx}"]
+        p32 = pk.SrcPlan(int(L), int(M), np.float32)
+        out = p32.run_host(x.astype(np.float32))[0]
+        assert o.full_scale_err(out, y) <= TOL_F32_SRC, (idx, L, M, N)
+        # tiled and generic kernels agree with the reference on device tensors too
+        for dt, tol in ((torch.float32, TOL_F32_SRC), (torch.float64, 1e-12)):
+            plan = p32 if dt == torch.float32 else pk.SrcPlan(int(L), int(M), np.float64)
+            xt = torch.as_tensor(np.stack([x, -0.5 * x]).astype(np.float64), device="cuda").to(dt)
+            a = plan.run(xt).cpu().numpy()
+            b = plan.run(xt, force_generic=True).cpu().numpy()
+            assert o.full_scale_err(a[0], y) <= tol and o.full_scale_err(b[0], y) <= tol
+            assert o.full_scale_err(a[1], -0.5 * y) <= tol
+
+
+@pytest.mark.parametrize("L,M,n_in,channels", [
+    (160, 147, 4410, 5), (160, 147, 4411, 130), (3, 2, 5003, 129), (2, 3, 4096, 7),
+    (8, 8, 1000, 3), (1, 8, 9000, 2), (8, 1, 777, 33), (147, 160, 3000, 2), (7, 5, 2048, 64),
+])
+def test_src_batched_vs_oracle(pk, torch_cuda, L, M, n_in, channels):
+    torch = torch_cuda
+    rng = np.random.default_rng(L * 1000 + M)
+    x = rng.uniform(-0.5, 0.5, (channels, n_in))
+    ref = np.stack([o.resample_closed_form(x[c], 44100, M, L)[0] for c in range(min(channels, 4))])
+    for dt, tol in ((np.float64, TOL_F64), (np.float32, TOL_F32_SRC)):
+        plan = pk.SrcPlan(L, M, dt)
+        xt = torch.as_tensor(x.astype(dt), device="cuda")
+        y = plan.run(xt).cpu().numpy()
+        assert y.shape == (channels, plan.out_len(n_in))
+        err = o.rel_err(y[:ref.shape[0]], ref) if dt == np.float64 else o.full_scale_err(y[:ref.shape[0]], ref)
+        assert err <= tol, (dt, plan.kernel_kind(channels, n_in), err)
+        # last channel too (exercises the partial channel tile)
+        last = o.resample_closed_form(x[-1], 44100, M, L)[0]
+        assert o.full_scale_err(y[-1], last) <= max(tol, 1e-12)
+        # a strided (non 16-byte aligned) view goes through the non-TMA loader
+        xo = torch.zeros((channels, n_in + 3), dtype=xt.dtype, device="cuda")
+        xo[:, 1:n_in + 1] = xt
+        y2 = plan.run(xo[:, 1:n_in + 1]).cpu().numpy()
+        assert np.max(np.abs(y2 - y)) <= 1e-6 if dt == np.float32 else np.max(np.abs(y2 - y)) <= 1e-13
+
+
+def test_src_known_answers(pk, torch_cuda):
+    torch = torch_cuda
+    plan = pk.SrcPlan(160, 147, np.float64)
+    # DC: unit gain away from the edges (sum(h) * L / L = 1)
+    y = plan.run(torch.ones((2, 2000), dtype=torch.float64, device="cuda")).cpu().numpy()
+    assert np.max(np.abs(y[:, 100:-100] - 1.0)) < 2e-3
+    # impulse: the decimated taps h[m*M + P - i*L]
+    x = np.zeros(600); x[300] = 1.0
+    y = plan.run(torch.as_tensor(x[None, :], device="cuda")).cpu().numpy()[0]
+    h = o.src_filter(160, 147)
+    T, P, _, n_out = o.src_geometry(600, 160, 147)
+    idx = np.arange(n_out) * 147 + P - 300 * 160
+    exp = np.where((idx >= 0) & (idx < T), h[np.clip(idx, 0, T - 1)], 0.0)
+    assert np.max(np.abs(y - exp)) <= 1e-15
+
+
+def test_src_c2_full_size_properties(pk, torch_cuda):
+    """Config C2 at full size: 1024 ch x 441000 -> 480000, fp32."""
+    torch = torch_cuda
+    ch, n_in = 1024, 441000
+    plan = pk.SrcPlan(160, 147, np.float32)
+    assert plan.kernel_kind(ch, n_in) == "tiled"
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand((ch, n_in), generator=gen, device="cuda", dtype=torch.float32) - 0.5
+    y = plan.run(x)
+    assert y.shape == (ch, 480000)
+    # oracle on a few whole channels, including the first/last of channel tiles
+    for c in (0, 127, 128, 1023):
+        ref = o.resample_closed_form(x[c].cpu().numpy().astype(np.float64), 44100, 147, 160)[0]
+        assert o.full_scale_err(y[c].cpu().numpy(), ref) <= TOL_F32_SRC
+    # linearity: SRC(a*x1 + b*x2) = a*SRC(x1) + b*SRC(x2)
+    x2 = torch.flip(x, dims=(0,))
+    y2 = plan.run(x2)
+    ymix = plan.run(0.25 * x + 0.75 * x2)
+    assert float((ymix - (0.25 * y + 0.75 * y2)).abs().max()) <= 5e-6
+    # DC in, DC out away from the clip edges
+    ydc = plan.run(torch.full((ch, n_in), 0.5, device="cuda"))
+    assert float((ydc[:, 64:-64] - 0.5).abs().max()) <= 2e-3
+
+
+# ------------------------------------------------------------------- EQ ----
+def test_eq_golden_dropin(dc, golden_eq):
+    g = golden_eq
+    for idx, row in enumerate(g["cases"]):
+        fs, gs = row[0], row[1:]
+        x, z = g[f"x_{idx}"], g[f"z_{idx}"]
+        out = dc.sistema_ecualizador(x, fs, gains_dict(gs))
+        assert (out is x) == bool(g[f"alias_{idx}"]), idx
+        if out is x:
+            continue
+        assert out.dtype == z.dtype and out.shape == z.shape, idx
+        assert o.rel_err(out, z) <= TOL_F64, (idx, row)
+    x = g["x_unknown"]
+    out = dc.sistema_ecualizador(x, 48000, {"Sub-Bass": 4, "Air": -7, "Brilliance": 5})
+    assert o.rel_err(out, g["z_unknown"]) <= TOL_F64
+    bands = ["Sub-Bass", "Bass", "Low Mids", "High Mids", "Presence", "Brilliance"]
+    rev = gains_dict(C1_GAINS[::-1], bands[::-1])
+    assert o.rel_err(dc.sistema_ecualizador(x, 48000, rev), g["z_reversed"]) <= TOL_F64
+    b, a = g["ba_lf"][:3], g["ba_lf"][3:]
+    assert o.rel_err(dc.aplicar_ecuacion_diferencias(g["x_lf"], b, a), g["y_lf"]) <= TOL_F64
+
+
+def test_eq_golden_f32(pk, golden_eq):
+    g = golden_eq
+    for idx, row in enumerate(g["cases"]):
+        fs, gs = row[0], row[1:]
+        if bool(g[f"alias_{idx}"]):
+            continue
+        plan = pk.EqPlan.from_gains(fs, gains_dict(gs), np.float32)
+        out = plan.run_host(g[f"x_{idx}"].astype(np.float32))[0]
+        assert o.full_scale_err(out, g[f"z_{idx}"]) <= TOL_F32_EQ, (idx, row)
+
+
+@pytest.mark.parametrize("gains", [C1_GAINS, (15,) * 6, (-15,) * 6, (-12.0412, 15, -12.5, 6, 0, -3)])
+@pytest.mark.parametrize("n", [1, 31, 1024, 1025, 48000 * 3 + 7])
+def test_eq_batched_vs_oracle(pk, torch_cuda, gains, n):
+    torch = torch_cuda
+    rng = np.random.default_rng(n)
+    channels = 19
+    x = rng.uniform(-0.25, 0.25, (channels, n))
+    gd = gains_dict(gains)
+    ref = np.stack([o.equalizer(x[c], 48000, gd) for c in range(channels)])
+    for dt in (np.float64, np.float32):
+        plan = pk.EqPlan.from_gains(48000, gd, dt)
+        xt = torch.as_tensor(x.astype(dt), device="cuda")
+        z = plan.run(xt)
+        if dt == np.float64:
+            assert o.rel_err(z.cpu().numpy(), ref) <= TOL_F64
+        else:
+            assert o.full_scale_err(z.cpu().numpy(), ref) <= TOL_F32_EQ
+        # in place, and through a misaligned view (scalar loader)
+        zi = xt.clone()
+        plan.run(zi, out=zi)
+        assert torch.equal(zi, z)
+        xo = torch.zeros((channels, n + 3), dtype=xt.dtype, device="cuda")
+        xo[:, 1:n + 1] = xt
+        z2 = plan.run(xo[:, 1:n + 1])
+        assert float((z2 - z).abs().max()) <= (1e-12 if dt == np.float64 else 1e-5)
+
+
+def test_eq_long_stream_c3_shape(pk, torch_cuda):
+    """C3's time axis (60 s @ 48 kHz = 2.88 M samples) on a handful of channels,
+    both gain sets of SURVEY 8d, fp32 and fp64."""
+    torch = torch_cuda
+    n = 2_880_000
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-0.25, 0.25, (4, n))
+    for gains in (C1_GAINS, (15,) * 6):
+        gd = gains_dict(gains)
+        ref = np.stack([o.equalizer(x[c], 48000, gd) for c in range(4)])
+        z64 = pk.EqPlan.from_gains(48000, gd, np.float64).run(torch.as_tensor(x, device="cuda")).cpu().numpy()
+        assert o.rel_err(z64, ref) <= TOL_F64
+        z32 = pk.EqPlan.from_gains(48000, gd, np.float32).run(
+            torch.as_tensor(x.astype(np.float32), device="cuda")).cpu().numpy()
+        assert o.full_scale_err(z32, ref) <= TOL_F32_EQ
+
+
+def test_eq_many_sections_and_corners(pk, dc, torch_cuda):
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-0.3, 0.3, 5000)
+    # 11 active entries (unknown keys map to 1 kHz): more than one fused pass
+    gains = {f"band{i}": (-1) ** i * (1 + i) for i in range(11)}
+    ref = o.equalizer(x, 48000, gains)
+    assert o.rel_err(dc.sistema_ecualizador(x, 48000, gains), ref) <= TOL_F64
+    # |g| == 0.1 everywhere: a clipped copy in the input dtype, no filtering
+    g01 = gains_dict((0.1,) * 6)
+    big = (3 * x).astype(np.float32)
+    out = dc.sistema_ecualizador(big, 48000, g01)
+    assert out.dtype == np.float32 and np.array_equal(out, np.clip(big, -1, 1))
+    # clamp: at fs = 8 kHz Presence and Brilliance both become 3600 Hz sections
+    assert o.rel_err(dc.sistema_ecualizador(x, 8000, gains_dict(C1_GAINS)),
+                     o.equalizer(x, 8000, gains_dict(C1_GAINS))) <= TOL_F64
+    # state-space description: DC gain of every section is 1 (peaking EQ)
+    plan = pk.EqPlan.from_gains(48000, gains_dict(C1_GAINS), np.float64)
+    for a00, a01, a10, a11, b0, b1, c0, c1, d in plan.describe():
+        A = np.array([[a00, a01], [a10, a11]])
+        dc_gain = np.array([c0, c1]) @ np.linalg.solve(np.eye(2) - A, np.array([b0, b1])) + d
+        assert abs(dc_gain - 1.0) < 1e-9
+
+
+# ------------------------------------------------------------------ FFT ----
+def test_fft_golden_dropin(dc, golden_fft):
+    g = golden_fft
+    for n in (1, 2, 4, 8, 16, 64, 256, 1024, 2048, 4096):
+        for kind in ("r", "c"):
+            x, X = g[f"x{kind}_{n}"], g[f"X{kind}_{n}"]
+            out = dc.fft_diezmado_en_tiempo(x)
+            if n == 1:
+                assert out is x
+                continue
+            assert out.dtype == np.complex128 and out.shape == X.shape
+            assert o.rel_err(out, X) <= TOL_F64, (n, kind)
+    for bad in (3, 6, 12, 100):
+        with pytest.raises(ValueError):
+            dc.fft_diezmado_en_tiempo(np.zeros(bad))
+
+
+def test_fft_large_c2c_and_real(pk, dc, golden_fft, torch_cuda):
+    torch = torch_cuda
+    rng = np.random.default_rng(5)
+    for n in (8192, 16384, 65536):
+        x = rng.normal(size=n) + 1j * rng.normal(size=n)
+        assert o.rel_err(dc.fft_diezmado_en_tiempo(x), np.fft.fft(x)) <= TOL_F64, n
+    # 2^16-point real magnitude against the golden vector from the reference FFT
+    x = golden_fft["xr_65536"].astype(np.float64)
+    for dt, tol in ((np.float64, TOL_F64), (np.float32, TOL_F32_FFT)):
+        plan = pk.FftPlan(65536, dt, hann=False)
+        mag = plan.magnitudes_host(x.astype(dt))[0, 0]
+        assert o.rel_err(mag, golden_fft["Xr_65536_mag"]) <= tol
+
+
+def test_spectrum_golden_dropin(dc, golden_spectrum):
+    g = golden_spectrum
+    for n in g["ok_lens"]:
+        x = g[f"x_{n}"]
+        f, m = dc.calcular_espectro_magnitud(x, 48000)
+        assert f.shape == g[f"f_{n}"].shape and m.shape == g[f"m_{n}"].shape, n
+        assert np.allclose(f, g[f"f_{n}"], rtol=0, atol=1e-9)
+        ref = g[f"m_{n}"]
+        if np.isnan(ref).any():
+            assert np.isnan(m).all()
+        else:
+            assert np.max(np.abs(m - ref)) <= TOL_F64 * max(1.0, np.max(np.abs(ref))), n
+    for n in g["valueerror_lens"]:
+        with pytest.raises(ValueError):
+            dc.calcular_espectro_magnitud(np.zeros(int(n)), 48000)
+
+
+@pytest.mark.parametrize("n_fft", [32, 64, 512, 2048, 4096, 16384, 65536])
+def test_fftmag_frames_vs_oracle(pk, torch_cuda, n_fft):
+    torch = torch_cuda
+    rng = np.random.default_rng(n_fft)
+    channels, n_frames = 3, 3
+    n = n_fft * n_frames + 17
+    x = rng.uniform(-1, 1, (channels, n))
+    w = o.hann_symmetric(n_fft)
+    ref = np.abs(np.fft.rfft(x[:, :n_fft * n_frames].reshape(channels, n_frames, n_fft) * w, axis=-1))
+    if n_fft <= 4096:   # the reference's own FFT on one frame pins np.fft as the stand-in
+        one = np.abs(o.fft_dit_recursive(x[0, :n_fft] * w))[:n_fft // 2 + 1]
+        assert o.rel_err(ref[0, 0], one) <= 1e-13
+    for dt, tol in ((np.float64, TOL_F64), (np.float32, TOL_F32_FFT)):
+        plan = pk.FftPlan(n_fft, dt, hann=True)
+        xt = torch.as_tensor(x.astype(dt), device="cuda")
+        mag = plan.magnitudes(xt).cpu().numpy()
+        assert mag.shape == ref.shape
+        for c in range(channels):
+            for f in range(n_frames):
+                assert o.rel_err(mag[c, f], ref[c, f]) <= tol, (dt, c, f)
+        # hop/offset (odd offset = misaligned loads) and zero padding past n_valid
+        m2 = plan.magnitudes(xt, hop=n_fft // 2, offset=3, n_frames=2, n_valid=n_fft + 5).cpu().numpy()
+        xz = np.zeros((channels, 4 * n_fft)); xz[:, :n_fft + 5] = x[:, :n_fft + 5]
+        for f in range(2):
+            s = 3 + f * (n_fft // 2)
+            r2 = np.abs(np.fft.rfft(xz[:, s:s + n_fft] * w, axis=-1))
+            assert o.rel_err(m2[:, f], r2) <= tol
+
+
+def test_fft_parseval_and_linearity_full_c4_frame_count(pk, torch_cuda):
+    """A slice of C4 (2^16-point frames of 2^20-sample clips): 64 channels x 16
+    frames, fp32 -- Parseval against the time-domain energy of each frame."""
+    torch = torch_cuda
+    n_fft, channels = 65536, 64
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand((channels, 1 << 20), generator=gen, device="cuda") * 2 - 1
+    plan = pk.FftPlan(n_fft, np.float32, hann=True)
+    mag = plan.magnitudes(x)
+    assert mag.shape == (channels, 16, n_fft // 2 + 1)
+    w = torch.as_tensor(o.hann_symmetric(n_fft), device="cuda")
+    frames = x.view(channels, 16, n_fft).double() * w
+    energy_t = (frames ** 2).sum(-1)
+    m = mag.double()
+    energy_f = (2 * (m ** 2).sum(-1) - m[..., 0] ** 2 - m[..., -1] ** 2) / n_fft
+    assert float(((energy_f - energy_t).abs() / energy_t).max()) <= 1e-4
+    ref = torch.fft.rfft(frames[:2], dim=-1).abs()
+    assert float((mag[:2].double() - ref).abs().max() / ref.max()) <= TOL_F32_FFT
+
+
+# ---------------------------------------------------------------- chain ----
+def test_chain_c1_golden(dc, pk, golden_chain, torch_cuda):
+    torch = torch_cuda
+    g = golden_chain
+    x = g["x"]
+    gd = gains_dict(C1_GAINS)
+    y, fs2 = dc.conversion_tasa_muestreo(x, 44100, 2, 3)
+    z = dc.sistema_ecualizador(y, fs2, gd)
+    assert fs2 == int(g["fs2"])
+    assert o.rel_err(y[:4096], g["y_head"]) <= TOL_F64 and o.rel_err(y[-4096:], g["y_tail"]) <= TOL_F64
+    assert o.rel_err(z[:4096], g["z_head"]) <= TOL_F64 and o.rel_err(z[-4096:], g["z_tail"]) <= TOL_F64
+    f, m = dc.calcular_espectro_magnitud(z[:100000], fs2)
+    assert o.rel_err(m, g["m_app"]) <= TOL_F64 and np.allclose(f, g["f_app"])
+    mid = len(z) // 2
+    frame = pk.FftPlan(4096, np.float64).magnitudes_host(z, offset=mid, n_frames=1)[0, 0]
+    assert o.rel_err(frame, g["mag4096"]) <= TOL_F64
+    # batched chain object, fp64 and fp32, device and host forms
+    yo, zo, mo, _ = o.chain(x.astype(np.float64), 44100, 2, 3, gd, n_fft=4096)
+    for dt, ty, tz, tm in ((np.float64, TOL_F64, TOL_F64, TOL_F64), (np.float32, TOL_F32_SRC, TOL_F32_EQ, 1e-4)):
+        ch = pk.Chain(3, 2, 44100, gd, n_fft=4096, dtype=dt)
+        xt = torch.as_tensor(np.stack([x, x[::-1]]).astype(dt), device="cuda")
+        yd, zd, md = ch.run(xt, keep_y=True)
+        assert o.full_scale_err(yd[0].cpu().numpy(), yo) <= ty
+        assert o.full_scale_err(zd[0].cpu().numpy(), zo) <= tz
+        assert o.rel_err(md[0].cpu().numpy(), mo) <= tm
+        zh, mh = ch.run_host(np.stack([x, x[::-1]]).astype(dt))
+        assert np.array_equal(zh, zd.cpu().numpy()) and np.array_equal(mh, md.cpu().numpy())
+        _, z2, m2 = ch.run(xt, keep_y=False)
+        assert torch.equal(z2, zd) and torch.equal(m2, md)
+
+
+def test_chain_c5_shape_slice(pk, torch_cuda):
+    """C5's clip shape (10 s @ 44.1 kHz -> 48 kHz, 6-band EQ, 4096-point frames)
+    on 256 clips; oracle on two clips, round-trip properties on the rest."""
+    torch = torch_cuda
+    gd = gains_dict(C1_GAINS)
+    ch = pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float32)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.rand((256, 441000), generator=gen, device="cuda") - 0.5
+    _, z, mag = ch.run(x)
+    assert z.shape == (256, 480000) and mag.shape == (256, 117, 2049)
+    assert float(z.abs().max()) <= 1.0
+    for c in (0, 255):
+        yo, zo, mo, _ = o.chain(x[c].cpu().numpy().astype(np.float64), 44100, 147, 160, gd, n_fft=4096)
+        assert o.full_scale_err(z[c].cpu().numpy(), zo) <= TOL_F32_EQ
+        assert o.rel_err(mag[c].cpu().numpy(), mo) <= 1e-4
+    # Parseval per frame ties the spectra back to z
+    w = torch.as_tensor(o.hann_symmetric(4096), device="cuda")
+    fr = z[:, :117 * 4096].view(256, 117, 4096).double() * w
+    et = (fr ** 2).sum(-1)
+    m = mag.double()
+    ef = (2 * (m ** 2).sum(-1) - m[..., 0] ** 2 - m[..., -1] ** 2) / 4096
+    assert float(((ef - et).abs() / et).max()) <= 1e-4
+
+
+def test_library_reports_launches(pk):
+    from dsp_audio_project_b200 import _lib
+    assert _lib.launch_count() > 0
