@@ -139,6 +139,8 @@ src_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SrcTiledArgs<T>
     const long long k0 = g0 / a.GP;
     const int gi0 = static_cast<int>(g0 - k0 * a.GP);
     lo = k0 * a.PI + s_tile_lo[gi0];
+    // TMA needs the box to start on a 16-byte boundary of the row: round the window start down
+    lo -= (lo & static_cast<long long>(16 / sizeof(T) - 1));
   };
   auto issue = [&](long long tile, int stage) {
     int ct, tt;
@@ -394,7 +396,7 @@ static void build_tiled(const std::vector<double>& h, int L, int M, int smem_lim
       for (int t = 0; t < GT; ++t) {
         const int gl = gi0 + t;
         const int64_t in_lo = static_cast<int64_t>(gl / g.GP) * g.PI + info[static_cast<size_t>(gl % g.GP)].lo;
-        span = std::max(span, static_cast<int>(in_lo - lo) + W + 3);
+        span = std::max(span, static_cast<int>(in_lo - lo) + W + 3 + (vec - 1));
       }
     }
     int pitch = static_cast<int>(round_up(span, vec));

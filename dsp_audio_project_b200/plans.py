@@ -66,6 +66,11 @@ def _check_tensor(t, dtype_id, name):
         raise ValueError(f"{name} must be [channels, time] with unit time stride")
 
 
+def _row_stride(t) -> int:
+    """Element stride between channels (a single-row tensor may carry any stride)."""
+    return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
+
+
 def _as_host(x, dtype_id, name="x"):
     a = np.ascontiguousarray(x, dtype=_np_dtype(dtype_id))
     if a.ndim == 1:
@@ -121,7 +126,7 @@ class SrcPlan:
         suffix = "f32" if self.dtype_id == F32 else "f64"
         fn = getattr(lib, ("dspb200_src_run_generic_" if force_generic else "dspb200_src_run_") + suffix)
         with torch.cuda.device(x.device):
-            check(fn(self._h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n_in,
+            check(fn(self._h, x.data_ptr(), _row_stride(x), out.data_ptr(), _row_stride(out), ch, n_in,
                      _stream_ptr(x)))
         return out
 
@@ -204,7 +209,7 @@ class EqPlan:
         ch, n = x.shape
         fn = _lib.load().dspb200_eq_run_f32 if self.dtype_id == F32 else _lib.load().dspb200_eq_run_f64
         with torch.cuda.device(x.device):
-            check(fn(self._h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, _stream_ptr(x)))
+            check(fn(self._h, x.data_ptr(), _row_stride(x), out.data_ptr(), _row_stride(out), ch, n, _stream_ptr(x)))
         return out
 
     def run_host(self, x):
@@ -267,7 +272,7 @@ class FftPlan:
         ws, ws_bytes = self._workspace(ch * n_frames, x.device)
         fn = _lib.load().dspb200_fftmag_run_f32 if self.dtype_id == F32 else _lib.load().dspb200_fftmag_run_f64
         with torch.cuda.device(x.device):
-            check(fn(self._h, x.data_ptr(), x.stride(0), n_valid, int(offset), hop, n_frames, out.data_ptr(),
+            check(fn(self._h, x.data_ptr(), _row_stride(x), n_valid, int(offset), hop, n_frames, out.data_ptr(),
                      self.bins, n_frames * self.bins, ch, ws, ws_bytes, _stream_ptr(x)))
         return out
 
@@ -344,7 +349,7 @@ class Chain:
         fn = lib.dspb200_chain_run_f32 if self.dtype_id == F32 else lib.dspb200_chain_run_f64
         with torch.cuda.device(x.device):
             check(fn(self.src._h if self.src else None, self.eq._h if self.eq else None, self.fft._h,
-                     x.data_ptr(), x.stride(0), ch, n_in, y.data_ptr() if y is not None else None,
+                     x.data_ptr(), _row_stride(x), ch, n_in, y.data_ptr() if y is not None else None,
                      z.data_ptr(), mag.data_ptr(), self._ws.data_ptr() if need.value else None,
                      need.value, _stream_ptr(x)))
         return y, z, mag
