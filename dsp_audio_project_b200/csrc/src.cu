@@ -29,6 +29,7 @@
 // sizeof(T)*(n_in + n_out) per channel; 40 FMA per output -> 10.4 flop/B fp32,
 // i.e. HBM and the FP32 pipe are co-critical.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -69,6 +70,7 @@ template <typename T> struct SrcTiledArgs {
   int n_tt;              // time tiles per channel tile
   long long n_tiles;
   int y_vec_ok;          // y rows are 16-byte aligned
+  int tma_store;         // outputs leave through TMA (swizzled staging in the consumed stage)
 };
 
 template <typename T, int RC> struct Acc;
@@ -100,10 +102,98 @@ template <int RC> struct Acc<double, RC> {
   __device__ __forceinline__ double get(int r, int c) const { return a[r][c]; }
 };
 
+// Rank-1 update over one group's window: acc[8][RC] += taps[pos][8] (x) x[RC][pos].
+template <typename T, int RC>
+__device__ __forceinline__ void src_group_mac(Acc<T, RC>& acc, const T* __restrict__ tab,
+                                              const T* __restrict__ xrow, size_t slot_stride, int nquads) {
+  acc.zero();
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll 1
+    for (int qd = 0; qd < nquads; ++qd) {
+      float4 xv[RC];
+#pragma unroll
+      for (int c = 0; c < RC; ++c)
+        xv[c] = *reinterpret_cast<const float4*>(xrow + c * slot_stride + 4 * qd);
+      const float4* tp = reinterpret_cast<const float4*>(tab + static_cast<size_t>(qd) * 4 * kRM);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 t0 = tp[2 * e], t1 = tp[2 * e + 1];
+#pragma unroll
+        for (int c = 0; c < RC; ++c) {
+          const float xe = e == 0 ? xv[c].x : (e == 1 ? xv[c].y : (e == 2 ? xv[c].z : xv[c].w));
+          acc.step(t0, t1, xe, c);
+        }
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int qd = 0; qd < nquads; ++qd) {
+      double xv[RC][4];
+#pragma unroll
+      for (int c = 0; c < RC; ++c) {
+        const double2 lo2 = *reinterpret_cast<const double2*>(xrow + c * slot_stride + 4 * qd);
+        const double2 hi2 = *reinterpret_cast<const double2*>(xrow + c * slot_stride + 4 * qd + 2);
+        xv[c][0] = lo2.x; xv[c][1] = lo2.y; xv[c][2] = hi2.x; xv[c][3] = hi2.y;
+      }
+      const double2* tp = reinterpret_cast<const double2*>(tab + static_cast<size_t>(qd) * 4 * kRM);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        double t[kRM];
+#pragma unroll
+        for (int r = 0; r < kRM / 2; ++r) {
+          const double2 tt2 = tp[4 * e + r];
+          t[2 * r] = tt2.x;
+          t[2 * r + 1] = tt2.y;
+        }
+#pragma unroll
+        for (int c = 0; c < RC; ++c)
+#pragma unroll
+          for (int r = 0; r < kRM; ++r) acc.a[r][c] = fma(t[r], xv[c][e], acc.a[r][c]);
+      }
+    }
+  }
+}
+
+// Direct register -> global stores: 8 consecutive outputs per channel slot.
+template <typename T, int RC>
+__device__ __forceinline__ void src_store_direct(const Acc<T, RC>& acc, const SrcTiledArgs<T>& a, int ct,
+                                                 int lane, long long m0) {
+#pragma unroll
+  for (int c = 0; c < RC; ++c) {
+    const long long ch = static_cast<long long>(ct) * a.CH + c * 32 + lane;
+    if (ch < a.channels) {
+      T* yp = a.y + ch * a.y_stride + m0;
+      if (a.y_vec_ok && m0 + kRM <= a.n_out) {
+        if constexpr (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(yp) = make_float4(acc.get(0, c), acc.get(1, c), acc.get(2, c), acc.get(3, c));
+          *reinterpret_cast<float4*>(yp + 4) = make_float4(acc.get(4, c), acc.get(5, c), acc.get(6, c), acc.get(7, c));
+        } else {
+#pragma unroll
+          for (int r = 0; r < kRM; r += 2)
+            *reinterpret_cast<double2*>(yp + r) = make_double2(acc.get(r, c), acc.get(r + 1, c));
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRM; ++r)
+          if (m0 + r < a.n_out) yp[r] = acc.get(r, c);
+      }
+    }
+  }
+}
+
+// kTma = true : warp-specialised.  Warps 0..GT-1 compute one output group each
+//   per tile; warp GT is the TMA producer: it streams the input windows into a
+//   two-stage ring (mbarrier full[]) and, when a.tma_store is set, writes each
+//   finished output tile back with TMA from the stage the tile was computed
+//   from (128-byte swizzled boxes, so the per-lane 16-byte shared-memory writes
+//   are conflict free and the global writes are full lines, clipped at the
+//   signal end by the tensor map).
+// kTma = false: plain cooperative loader for inputs TMA cannot describe.
 template <typename T, int RC, bool kTma>
-__global__ void __launch_bounds__(kSrcMaxWarps * 32, 1)
-src_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SrcTiledArgs<T> a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__((kSrcMaxWarps + (kTma ? 1 : 0)) * 32, 1)
+src_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
+                 const SrcTiledArgs<T> a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
   const size_t stage_elems = static_cast<size_t>(a.CH) * a.PITCH;
   T* xs0 = reinterpret_cast<T*>(smem);
   T* xs1 = xs0 + stage_elems;
@@ -112,11 +202,14 @@ src_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SrcTiledArgs<T>
   int* s_tile_lo = s_group_lo + a.GP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(s_tile_lo + a.GP) + 7) & ~static_cast<uintptr_t>(7));
+  uint64_t* full = bars;        // [2] input window landed (TMA complete_tx)
+  uint64_t* done = bars + 2;    // [2] consumers finished with the stage (outputs staged / window consumed)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int nthreads = blockDim.x;
+  constexpr int VEC = 16 / static_cast<int>(sizeof(T));
 
   for (int i = tid; i < a.GP * a.WROWS * kRM; i += nthreads) s_table[i] = a.table[i];
   for (int i = tid; i < a.GP; i += nthreads) {
@@ -124,62 +217,86 @@ src_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SrcTiledArgs<T>
     s_tile_lo[i] = a.tile_lo[i];
   }
   if (kTma && tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&done[0], a.GT);
+    mbar_init(&done[1], a.GT);
     fence_mbar_init();
-    tma_prefetch_desc(&tmap);
   }
   __syncthreads();
 
-  const uint32_t stage_bytes = static_cast<uint32_t>(stage_elems * sizeof(T));
-  auto tile_coords = [&](long long tile, int& ct, int& tt, long long& lo) {
+  auto tile_coords = [&](long long tile, int& ct, int& tt, int& lo) {
     ct = static_cast<int>(tile / a.n_tt);
     tt = static_cast<int>(tile - static_cast<long long>(ct) * a.n_tt);
-    const long long g0 = static_cast<long long>(tt) * a.GT;
-    const long long k0 = g0 / a.GP;
-    const int gi0 = static_cast<int>(g0 - k0 * a.GP);
+    const int g0 = tt * a.GT;
+    const int k0 = g0 / a.GP;
+    const int gi0 = g0 - k0 * a.GP;
     lo = k0 * a.PI + s_tile_lo[gi0];
-    // TMA needs the box to start on a 16-byte boundary of the row: round the window start down
-    lo -= (lo & static_cast<long long>(16 / sizeof(T) - 1));
-  };
-  auto issue = [&](long long tile, int stage) {
-    int ct, tt;
-    long long lo;
-    tile_coords(tile, ct, tt, lo);
-    T* dst = stage ? xs1 : xs0;
-    if constexpr (kTma) {
-      mbar_expect_tx(&bars[stage], stage_bytes);
-      tma_load_2d(dst, &tmap, static_cast<int>(lo), ct * a.CH, &bars[stage]);
-    }
+    lo -= (lo & (VEC - 1));   // TMA boxes must start on a 16-byte boundary of the row
   };
 
   const long long first = blockIdx.x;
   const long long step = gridDim.x;
+
   if constexpr (kTma) {
-    if (tid == 0) {
-      if (first < a.n_tiles) issue(first, 0);
-      if (first + step < a.n_tiles) issue(first + step, 1);
+    if (warp == a.GT) {
+      // ---------------- producer warp ----------------
+      if (lane == 0) {
+        const uint32_t stage_bytes = static_cast<uint32_t>(stage_elems * sizeof(T));
+        tma_prefetch_desc(&tmap);
+        if (a.tma_store) tma_prefetch_desc(&tmap_y);
+        auto issue = [&](long long tile, int stage) {
+          int ct, tt, lo;
+          tile_coords(tile, ct, tt, lo);
+          mbar_expect_tx(&full[stage], stage_bytes);
+          tma_load_2d(stage ? xs1 : xs0, &tmap, lo, ct * a.CH, &full[stage]);
+        };
+        if (first < a.n_tiles) issue(first, 0);
+        if (first + step < a.n_tiles) issue(first + step, 1);
+        constexpr int OUTS_PER_BOX = 128 / static_cast<int>(sizeof(T));
+        const int boxes = a.GT * kRM / OUTS_PER_BOX;
+        const size_t box_elems = static_cast<size_t>(a.CH) * OUTS_PER_BOX;
+        long long it = 0;
+        for (long long tile = first; tile < a.n_tiles; tile += step, ++it) {
+          const int stage = static_cast<int>(it & 1);
+          const uint32_t phase = static_cast<uint32_t>((it >> 1) & 1);
+          mbar_wait(&done[stage], phase);
+          if (a.tma_store) {
+            int ct, tt, lo;
+            tile_coords(tile, ct, tt, lo);
+            const T* src = stage ? xs1 : xs0;
+            for (int b = 0; b < boxes; ++b)
+              tma_store_2d(&tmap_y, src + b * box_elems, tt * a.GT * kRM + b * OUTS_PER_BOX, ct * a.CH);
+            tma_store_commit();
+            tma_store_wait_read0();   // the stage may be overwritten once TMA has read it
+          }
+          const long long nxt = tile + 2 * step;
+          if (nxt < a.n_tiles) issue(nxt, stage);
+        }
+        if (a.tma_store) tma_store_wait_all0();
+      }
+      return;
     }
   }
 
+  // ---------------- consumer warps ----------------
+  const size_t slot_stride = static_cast<size_t>(32) * a.PITCH;
   long long it = 0;
   for (long long tile = first; tile < a.n_tiles; tile += step, ++it) {
     const int stage = static_cast<int>(it & 1);
     const uint32_t phase = static_cast<uint32_t>((it >> 1) & 1);
     T* xs = stage ? xs1 : xs0;
-    int ct, tt;
-    long long tile_lo;
+    int ct, tt, tile_lo;
     tile_coords(tile, ct, tt, tile_lo);
     if constexpr (kTma) {
-      mbar_wait(&bars[stage], phase);
+      mbar_wait(&full[stage], phase);
     } else {
-      // plain loader for inputs TMA cannot describe (unaligned base or pitch)
       const int total = a.CH * a.PITCH;
       for (int i = tid; i < total; i += nthreads) {
         const int row = i / a.PITCH;
         const int col = i - row * a.PITCH;
         const long long ch = static_cast<long long>(ct) * a.CH + row;
-        const long long gi = tile_lo + col;
+        const long long gi = static_cast<long long>(tile_lo) + col;
         T v = T(0);
         if (ch < a.channels && gi >= 0 && gi < a.n_in) v = a.x[ch * a.x_stride + gi];
         xs[i] = v;
@@ -187,97 +304,56 @@ src_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SrcTiledArgs<T>
       __syncthreads();
     }
 
-    const long long G = static_cast<long long>(tt) * a.GT + warp;   // global output group
-    const long long m0 = G * kRM;
-    if (warp < a.GT && m0 < a.n_out) {
-      const long long k = G / a.GP;
-      const int gi = static_cast<int>(G - k * a.GP);
-      const int off = static_cast<int>(k * a.PI + s_group_lo[gi] - tile_lo);
+    const int G = tt * a.GT + warp;   // global output group
+    const long long m0 = static_cast<long long>(G) * kRM;
+    const bool active = m0 < a.n_out;
+    Acc<T, RC> acc;
+    if (active) {
+      const int k = G / a.GP;
+      const int gi = G - k * a.GP;
+      const int off = k * a.PI + s_group_lo[gi] - tile_lo;
       const int phi = off & 3;
-      const int off4 = off - phi;
       const int nquads = (phi + a.W + 3) >> 2;
       const T* tab = s_table + (static_cast<size_t>(gi) * a.WROWS + (3 - phi)) * kRM;
-      const T* xrow = xs + static_cast<size_t>(lane) * a.PITCH + off4;
-      const size_t slot_stride = static_cast<size_t>(32) * a.PITCH;
-
-      Acc<T, RC> acc;
-      acc.zero();
-      if constexpr (sizeof(T) == 4) {
-#pragma unroll 1
-        for (int qd = 0; qd < nquads; ++qd) {
-          float4 xv[RC];
-#pragma unroll
-          for (int c = 0; c < RC; ++c)
-            xv[c] = *reinterpret_cast<const float4*>(xrow + c * slot_stride + 4 * qd);
-          const float4* tp = reinterpret_cast<const float4*>(tab + static_cast<size_t>(qd) * 4 * kRM);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 t0 = tp[2 * e], t1 = tp[2 * e + 1];
-#pragma unroll
-            for (int c = 0; c < RC; ++c) {
-              const float xe = e == 0 ? xv[c].x : (e == 1 ? xv[c].y : (e == 2 ? xv[c].z : xv[c].w));
-              acc.step(t0, t1, xe, c);
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int qd = 0; qd < nquads; ++qd) {
-          double xv[RC][4];
-#pragma unroll
-          for (int c = 0; c < RC; ++c) {
-            const double2 lo2 = *reinterpret_cast<const double2*>(xrow + c * slot_stride + 4 * qd);
-            const double2 hi2 = *reinterpret_cast<const double2*>(xrow + c * slot_stride + 4 * qd + 2);
-            xv[c][0] = lo2.x; xv[c][1] = lo2.y; xv[c][2] = hi2.x; xv[c][3] = hi2.y;
-          }
-          const double2* tp = reinterpret_cast<const double2*>(tab + static_cast<size_t>(qd) * 4 * kRM);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            double t[kRM];
-#pragma unroll
-            for (int r = 0; r < kRM / 2; ++r) {
-              const double2 tt2 = tp[4 * e + r];
-              t[2 * r] = tt2.x;
-              t[2 * r + 1] = tt2.y;
-            }
-#pragma unroll
-            for (int c = 0; c < RC; ++c)
-#pragma unroll
-              for (int r = 0; r < kRM; ++r) acc.a[r][c] = fma(t[r], xv[c][e], acc.a[r][c]);
-          }
-        }
-      }
-
-      // store: 8 consecutive outputs per channel slot
-#pragma unroll
-      for (int c = 0; c < RC; ++c) {
-        const long long ch = static_cast<long long>(ct) * a.CH + c * 32 + lane;
-        if (ch < a.channels) {
-          T* yp = a.y + ch * a.y_stride + m0;
-          if (a.y_vec_ok && m0 + kRM <= a.n_out) {
-            if constexpr (sizeof(T) == 4) {
-              *reinterpret_cast<float4*>(yp) = make_float4(acc.get(0, c), acc.get(1, c), acc.get(2, c), acc.get(3, c));
-              *reinterpret_cast<float4*>(yp + 4) = make_float4(acc.get(4, c), acc.get(5, c), acc.get(6, c), acc.get(7, c));
-            } else {
-#pragma unroll
-              for (int r = 0; r < kRM; r += 2)
-                *reinterpret_cast<double2*>(yp + r) = make_double2(acc.get(r, c), acc.get(r + 1, c));
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < kRM; ++r)
-              if (m0 + r < a.n_out) yp[r] = acc.get(r, c);
-          }
-        }
-      }
+      const T* xrow = xs + static_cast<size_t>(lane) * a.PITCH + (off - phi);
+      src_group_mac<T, RC>(acc, tab, xrow, slot_stride, nquads);
     }
 
-    __syncthreads();  // every warp is done with this stage
     if constexpr (kTma) {
-      if (tid == 0) {
-        const long long nxt = tile + 2 * step;
-        if (nxt < a.n_tiles) issue(nxt, stage);
+      if (a.tma_store) {
+        // every consumer is done reading this stage -> reuse it as the output tile
+        asm volatile("bar.sync 1, %0;" ::"r"(a.GT * 32) : "memory");
+        if (active) {
+          constexpr int OUTS_PER_BOX = 128 / static_cast<int>(sizeof(T));
+          constexpr int GROUPS_PER_BOX = OUTS_PER_BOX / kRM;
+          constexpr int CHUNKS = kRM * static_cast<int>(sizeof(T)) / 16;   // 16-byte chunks per group
+          unsigned char* box = reinterpret_cast<unsigned char*>(xs) +
+                               static_cast<size_t>(warp / GROUPS_PER_BOX) * a.CH * 128;
+          const int chunk0 = (warp % GROUPS_PER_BOX) * CHUNKS;
+#pragma unroll
+          for (int c = 0; c < RC; ++c) {
+            const int row = c * 32 + lane;
+            unsigned char* rp = box + static_cast<size_t>(row) * 128;
+#pragma unroll
+            for (int q = 0; q < CHUNKS; ++q) {
+              void* dst = rp + (((chunk0 + q) ^ (row & 7)) << 4);
+              if constexpr (sizeof(T) == 4)
+                *reinterpret_cast<float4*>(dst) = make_float4(acc.get(4 * q, c), acc.get(4 * q + 1, c),
+                                                               acc.get(4 * q + 2, c), acc.get(4 * q + 3, c));
+              else
+                *reinterpret_cast<double2*>(dst) = make_double2(acc.get(2 * q, c), acc.get(2 * q + 1, c));
+            }
+          }
+          fence_proxy_async();
+        }
+      } else if (active) {
+        src_store_direct<T, RC>(acc, a, ct, lane, m0);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[stage]);
+    } else {
+      if (active) src_store_direct<T, RC>(acc, a, ct, lane, m0);
+      __syncthreads();  // every warp is done with this stage
     }
   }
 }
@@ -403,7 +479,7 @@ static void build_tiled(const std::vector<double>& h, int L, int M, int smem_lim
     while ((static_cast<size_t>(pitch) * sizeof(T)) % 128 != 16) pitch += vec;
     if (pitch > 256) continue;
     const size_t stage = static_cast<size_t>(g.CH) * pitch * sizeof(T);
-    const size_t total = 2 * stage + g.table_bytes + 2 * static_cast<size_t>(g.GP) * sizeof(int) + 64;
+    const size_t total = 2 * stage + g.table_bytes + 2 * static_cast<size_t>(g.GP) * sizeof(int) + 64;  // + 4 mbarriers
     if (total > static_cast<size_t>(smem_limit)) continue;
     g.GT = GT;
     g.PITCH = pitch;
@@ -453,24 +529,35 @@ int src_run(const dspb200_src_plan* plan, const T* x, int64_t xs, T* y, int64_t 
   const int vec = 16 / static_cast<int>(sizeof(T));
   a.y_vec_ok = (reinterpret_cast<uintptr_t>(y) % 16 == 0 && ys % vec == 0) ? 1 : 0;
   const bool tma_ok = reinterpret_cast<uintptr_t>(x) % 16 == 0 && (xs * sizeof(T)) % 16 == 0;
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_y;
   memset(&tmap, 0, sizeof(tmap));
+  memset(&tmap_y, 0, sizeof(tmap_y));
   if (tma_ok)
     DSP_TRY(encode_tmap_2d(&tmap, plan->dtype, x, static_cast<uint64_t>(n_in), static_cast<uint64_t>(channels),
                            static_cast<uint64_t>(xs) * sizeof(T), static_cast<uint32_t>(g.PITCH),
                            static_cast<uint32_t>(g.CH)));
+  // TMA store path: y rows 16-byte aligned, the output tile fits the consumed
+  // input stage, and the tile is a whole number of 128-byte swizzled boxes.
+  const int outs_per_box = 128 / static_cast<int>(sizeof(T));
+  a.tma_store = 0;
+  if (tma_ok && a.y_vec_ok && g.GT * kRM <= g.PITCH && (g.GT * kRM) % outs_per_box == 0 &&
+      getenv("DSPB200_SRC_NO_TMA_STORE") == nullptr) {
+    DSP_TRY(encode_tmap_2d(&tmap_y, plan->dtype, y, static_cast<uint64_t>(n_out), static_cast<uint64_t>(channels),
+                           static_cast<uint64_t>(ys) * sizeof(T), static_cast<uint32_t>(outs_per_box),
+                           static_cast<uint32_t>(g.CH), true));
+    a.tma_store = 1;
+  }
   const int64_t sms = sm_count();
   const int grid = static_cast<int>(a.n_tiles < sms ? a.n_tiles : sms);
-  const int threads = g.GT * 32;
   constexpr int RC = SrcCfg<T>::RC;
   if (tma_ok) {
     auto kern = src_tiled_kernel<T, RC, true>;
     DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem_bytes)));
-    kern<<<grid, threads, g.smem_bytes, stream>>>(tmap, a);
+    kern<<<grid, (g.GT + 1) * 32, g.smem_bytes, stream>>>(tmap, tmap_y, a);
   } else {
     auto kern = src_tiled_kernel<T, RC, false>;
     DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem_bytes)));
-    kern<<<grid, threads, g.smem_bytes, stream>>>(tmap, a);
+    kern<<<grid, g.GT * 32, g.smem_bytes, stream>>>(tmap, tmap_y, a);
   }
   return after_launch("src_tiled_kernel");
 }
