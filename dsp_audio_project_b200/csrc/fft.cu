@@ -112,7 +112,10 @@ template <typename T> struct FftArgs {
   int r_top;
   int n_pass;
   int radix[8];
-  const C* tw_sub;         // W_m[k]
+  const C* tw_pass;        // per-pass twiddle rows, pass p at tw_offset[p]: [ns_p][17], row[r] = W^(r k)
+  int tw_offset[8];
+  int tw_total;
+  int tw_in_smem;
   const C* tw_top;         // W_nc[k]
   const C* tw_post;        // W_(2nc)[k], k = 0..nc/2
   // output
@@ -121,45 +124,40 @@ template <typename T> struct FftArgs {
   long long n_items;       // transforms * r_top
 };
 
+// Thread t owns the 16 points  t + s*(m/16), s = 0..15, of a pass's input (a
+// coalesced / conflict-free access for consecutive t).  For radix R that is
+// B = 16/R butterflies; butterfly b takes its r-th operand from slot b + r*B.
 template <typename T, int R>
-__device__ __forceinline__ void load_pass(typename Cpx<T>::type* v, const typename Cpx<T>::type* s,
-                                          int t, int m) {
-  // thread t holds 16 points: B = 16/R butterflies of radix R
+__device__ __forceinline__ void gather_butterflies(typename Cpx<T>::type* v, const typename Cpx<T>::type* tmp) {
   constexpr int B = 16 / R;
 #pragma unroll
-  for (int b = 0; b < B; ++b) {
-    const int j = t + b * (m / 16);
+  for (int b = 0; b < B; ++b)
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[b * R + r] = s[padded(j + r * (m / R))];
-  }
+    for (int r = 0; r < R; ++r) v[b * R + r] = tmp[b + r * B];
 }
 
-template <typename T, int R, typename F>
-__device__ __forceinline__ void load_first(typename Cpx<T>::type* v, F& fetch, int t, int m) {
-  constexpr int B = 16 / R;
-#pragma unroll
-  for (int b = 0; b < B; ++b) {
-    const int j = t + b * (m / 16);
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[b * R + r] = fetch(j + r * (m / R));
-  }
-}
+constexpr int kTwPitch = 17;   // per-pass twiddle rows [k][17]: 16-lane 8-byte reads hit distinct banks
 
 template <typename T, int R>
-__device__ __forceinline__ void compute_store_pass(typename Cpx<T>::type* v, typename Cpx<T>::type* s,
+__device__ __forceinline__ void compute_store_pass(const typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
                                                    const typename Cpx<T>::type* __restrict__ tw, int t,
                                                    int m, int ns) {
   typedef typename Cpx<T>::type C;
   constexpr int B = 16 / R;
+  C v[16];
+  gather_butterflies<T, R>(v, tmp);
 #pragma unroll
   for (int b = 0; b < B; ++b) {
     const int j = t + b * (m / 16);
     const int k = j & (ns - 1);
     C* w = v + b * R;
     if (ns > 1) {
-      const int stride = m / (ns * R);
+      const C* row = tw + k * kTwPitch;      // row[r] = exp(-2 pi i r k / (ns R))
+      C wv[R];
 #pragma unroll
-      for (int r = 1; r < R; ++r) w[r] = cmul(w[r], tw[r * k * stride]);
+      for (int r = 1; r < R; ++r) wv[r] = row[r];
+#pragma unroll
+      for (int r = 1; r < R; ++r) w[r] = cmul(w[r], wv[r]);
     }
     Dft<T, R>::run(w);
     const int base = (j - k) * R + k;
@@ -168,63 +166,77 @@ __device__ __forceinline__ void compute_store_pass(typename Cpx<T>::type* v, typ
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void run_pass(int R, const typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
+                                         const typename Cpx<T>::type* tw, int t, int m, int ns) {
+  switch (R) {
+    case 16: compute_store_pass<T, 16>(tmp, s, tw, t, m, ns); break;
+    case 8: compute_store_pass<T, 8>(tmp, s, tw, t, m, ns); break;
+    case 4: compute_store_pass<T, 4>(tmp, s, tw, t, m, ns); break;
+    default: compute_store_pass<T, 2>(tmp, s, tw, t, m, ns); break;
+  }
+}
+
 // MODE 0: real frames -> magnitudes (r_top == 1)      MODE 1: real frames -> workspace
 // MODE 2: complex -> complex (r_top == 1)              MODE 3: complex -> workspace
-template <typename T, int MODE>
-__global__ void __launch_bounds__(512)
+template <typename T, int MODE, int MAXT>
+__global__ void __launch_bounds__(MAXT, (sizeof(T) == 4 ? (MAXT <= 128 ? 5 : (MAXT <= 256 ? 2 : 1)) : (MAXT <= 128 ? 2 : 1)))
 fft_stockham_kernel(const FftArgs<T> a) {
   typedef typename Cpx<T>::type C;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* s = reinterpret_cast<C*>(smem_raw);
   const int t = threadIdx.x;
   const int m = a.m;
-  const int nthr = m / 16;   // active threads
-  const bool active = t < nthr;
+  const int q16 = m / 16;
+  const bool active = t < q16;
   constexpr bool kReal = (MODE == 0 || MODE == 1);
+
+  // per-pass twiddle tables: shared memory when they fit, else straight from global (L1/L2)
+  const C* tw = a.tw_pass;
+  if (a.tw_in_smem) {
+    C* stw = s + padded(m) + 1;
+    for (int i = t; i < a.tw_total; i += blockDim.x) stw[i] = a.tw_pass[i];
+    tw = stw;
+    __syncthreads();
+  }
 
   for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const long long f = item / a.r_top;
     const int rho = static_cast<int>(item - f * a.r_top);
-    C v[16];
-    // ---- first pass: operands come straight from global memory -------------
-    const int R0 = a.radix[0];
-    const T* xrow = nullptr;
-    long long fstart = 0;
-    bool fast = false;
-    if constexpr (kReal) {
-      const long long c = f / a.n_frames;
-      const long long fr = f - c * a.n_frames;
-      xrow = a.x + c * a.x_stride;
-      fstart = a.offset + fr * a.hop;
-      fast = (fstart + 2LL * a.nc <= a.n_valid) && (((reinterpret_cast<uintptr_t>(xrow + fstart)) % (2 * sizeof(T))) == 0);
-    }
-    auto fetch = [&](int j) -> C {   // element j of sub-sequence rho
-      const long long i = static_cast<long long>(a.r_top) * j + rho;
-      C z;
+    C tmp[16];
+    // ---- first pass: operands come straight from global memory, all 16 loads in flight ----
+    if (active) {
       if constexpr (kReal) {
+        const long long c = f / a.n_frames;
+        const long long fr = f - c * a.n_frames;
+        const T* xrow = a.x + c * a.x_stride;
+        const long long fstart = a.offset + fr * a.hop;
+        const bool fast = (fstart + 2LL * a.nc <= a.n_valid) &&
+                          (((reinterpret_cast<uintptr_t>(xrow + fstart)) % (2 * sizeof(T))) == 0);
         if (fast) {
-          z = *reinterpret_cast<const C*>(xrow + fstart + 2 * i);
+          const C* xp = reinterpret_cast<const C*>(xrow + fstart);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (t + u * q16) + rho];
         } else {
-          const long long s0 = fstart + 2 * i;
-          z.x = s0 < a.n_valid ? xrow[s0] : T(0);
-          z.y = s0 + 1 < a.n_valid ? xrow[s0 + 1] : T(0);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const long long s0 = fstart + 2 * (static_cast<long long>(a.r_top) * (t + u * q16) + rho);
+            tmp[u].x = s0 < a.n_valid ? xrow[s0] : T(0);
+            tmp[u].y = s0 + 1 < a.n_valid ? xrow[s0 + 1] : T(0);
+          }
         }
         if (a.window) {
-          const C w = *reinterpret_cast<const C*>(a.window + 2 * i);
-          z.x *= w.x;
-          z.y *= w.y;
+          const C* wp = reinterpret_cast<const C*>(a.window);
+          C wv[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) wv[u] = wp[static_cast<long long>(a.r_top) * (t + u * q16) + rho];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) { tmp[u].x *= wv[u].x; tmp[u].y *= wv[u].y; }
         }
       } else {
-        z = reinterpret_cast<const C*>(a.x)[f * a.nc + i];
-      }
-      return z;
-    };
-    if (active) {
-      switch (R0) {
-        case 16: load_first<T, 16>(v, fetch, t, m); break;
-        case 8: load_first<T, 8>(v, fetch, t, m); break;
-        case 4: load_first<T, 4>(v, fetch, t, m); break;
-        default: load_first<T, 2>(v, fetch, t, m); break;
+        const C* xp = reinterpret_cast<const C*>(a.x) + f * a.nc;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (t + u * q16) + rho];
       }
     }
     __syncthreads();   // previous item's readers are done with s
@@ -233,23 +245,12 @@ fft_stockham_kernel(const FftArgs<T> a) {
       const int R = a.radix[pass];
       if (pass > 0) {
         if (active) {
-          switch (R) {
-            case 16: load_pass<T, 16>(v, s, t, m); break;
-            case 8: load_pass<T, 8>(v, s, t, m); break;
-            case 4: load_pass<T, 4>(v, s, t, m); break;
-            default: load_pass<T, 2>(v, s, t, m); break;
-          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) tmp[u] = s[padded(t + u * q16)];
         }
         __syncthreads();
       }
-      if (active) {
-        switch (R) {
-          case 16: compute_store_pass<T, 16>(v, s, a.tw_sub, t, m, ns); break;
-          case 8: compute_store_pass<T, 8>(v, s, a.tw_sub, t, m, ns); break;
-          case 4: compute_store_pass<T, 4>(v, s, a.tw_sub, t, m, ns); break;
-          default: compute_store_pass<T, 2>(v, s, a.tw_sub, t, m, ns); break;
-        }
-      }
+      if (active) run_pass<T>(R, tmp, s, tw + a.tw_offset[pass], t, m, ns);
       __syncthreads();
       ns *= R;
     }
@@ -377,7 +378,9 @@ fft_small_kernel(const FftArgs<T> a, const typename Cpx<T>::type* __restrict__ t
 struct FftSide {
   int nc = 0, m = 0, r_top = 1, n_pass = 0;
   int radix[8] = {0};
-  void* d_tw_sub = nullptr;
+  void* d_tw_pass = nullptr;
+  int tw_offset[8] = {0};
+  int tw_total = 0;
   void* d_tw_top = nullptr;
   void* d_tw_post = nullptr;
 };
@@ -425,7 +428,34 @@ static int build_side(FftSide& s, int nc, bool real) {
   s.n_pass = 0;
   if (rest > 1) s.radix[s.n_pass++] = rest;
   for (int i = 0; i < n16; ++i) s.radix[s.n_pass++] = 16;
-  DSP_TRY(upload_twiddles<T>(s.m, s.m, &s.d_tw_sub));
+  {
+    typedef typename Cpx<T>::type C;
+    std::vector<C> h;
+    int ns = 1;
+    for (int p = 0; p < s.n_pass; ++p) {
+      const int R = s.radix[p];
+      s.tw_offset[p] = static_cast<int>(h.size());
+      if (ns > 1) {
+        for (int k = 0; k < ns; ++k)
+          for (int r = 0; r < kTwPitch; ++r) {
+            C w; w.x = T(1); w.y = T(0);
+            if (r >= 1 && r < R) {
+              const long double ang = -2.0L * kPiL * static_cast<long double>(r) * static_cast<long double>(k) /
+                                      (static_cast<long double>(ns) * static_cast<long double>(R));
+              w.x = static_cast<T>(cosl(ang));
+              w.y = static_cast<T>(sinl(ang));
+            }
+            h.push_back(w);
+          }
+      }
+      ns *= R;
+    }
+    s.tw_total = static_cast<int>(h.size());
+    if (!h.empty()) {
+      DSP_CUDA(cudaMalloc(&s.d_tw_pass, h.size() * sizeof(C)));
+      DSP_CUDA(cudaMemcpy(s.d_tw_pass, h.data(), h.size() * sizeof(C), cudaMemcpyHostToDevice));
+    }
+  }
   if (s.r_top > 1) DSP_TRY(upload_twiddles<T>(nc, nc, &s.d_tw_top));
   if (real) DSP_TRY(upload_twiddles<T>(2 * nc, nc / 2 + 1, &s.d_tw_post));
   return DSPB200_OK;
@@ -465,16 +495,22 @@ static void fill_args(FftArgs<T>& a, const FftSide& s) {
   typedef typename Cpx<T>::type C;
   a.nc = s.nc; a.m = s.m; a.r_top = s.r_top; a.n_pass = s.n_pass;
   for (int i = 0; i < 8; ++i) a.radix[i] = s.radix[i];
-  a.tw_sub = static_cast<const C*>(s.d_tw_sub);
+  a.tw_pass = static_cast<const C*>(s.d_tw_pass);
+  for (int i = 0; i < 8; ++i) a.tw_offset[i] = s.tw_offset[i];
+  a.tw_total = s.tw_total;
+  a.tw_in_smem = 0;
   a.tw_top = static_cast<const C*>(s.d_tw_top);
   a.tw_post = static_cast<const C*>(s.d_tw_post);
 }
 
-template <typename T, int MODE>
-static int launch_stockham(const FftArgs<T>& a, cudaStream_t stream) {
+template <typename T, int MODE, int MAXT>
+static int launch_stockham_t(FftArgs<T> a, cudaStream_t stream) {
   typedef typename Cpx<T>::type C;
-  const size_t smem = static_cast<size_t>(padded(a.m) + 1) * sizeof(C);
-  auto kern = fft_stockham_kernel<T, MODE>;
+  size_t smem = static_cast<size_t>(padded(a.m) + 1) * sizeof(C);
+  const size_t tw_bytes = static_cast<size_t>(a.tw_total) * sizeof(C);
+  a.tw_in_smem = (tw_bytes > 0 && tw_bytes <= 24 * 1024) ? 1 : 0;   // small tables ride along in shared memory
+  if (a.tw_in_smem) smem += tw_bytes;
+  auto kern = fft_stockham_kernel<T, MODE, MAXT>;
   DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int threads = a.m / 16;
   if (threads < 32) threads = 32;
@@ -485,6 +521,14 @@ static int launch_stockham(const FftArgs<T>& a, cudaStream_t stream) {
   const int grid = static_cast<int>(a.n_items < cap ? a.n_items : cap);
   kern<<<grid, threads, smem, stream>>>(a);
   return after_launch("fft_stockham_kernel");
+}
+
+template <typename T, int MODE>
+static int launch_stockham(const FftArgs<T>& a, cudaStream_t stream) {
+  const int threads = a.m / 16;
+  if (threads <= 128) return launch_stockham_t<T, MODE, 128>(a, stream);
+  if (threads <= 256) return launch_stockham_t<T, MODE, 256>(a, stream);
+  return launch_stockham_t<T, MODE, 512>(a, stream);
 }
 
 template <typename T, bool kReal>
@@ -645,7 +689,7 @@ int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
   if (!p) return DSPB200_OK;
   FftSide* sides[2] = {&p->real_side, &p->c2c_side};
   for (FftSide* s : sides) {
-    cudaFree(s->d_tw_sub);
+    cudaFree(s->d_tw_pass);
     cudaFree(s->d_tw_top);
     cudaFree(s->d_tw_post);
   }
