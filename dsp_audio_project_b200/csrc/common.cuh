@@ -150,6 +150,26 @@ __device__ __forceinline__ void ffma2_bcast(float2& d, const float2 a, const flo
         "l"(*reinterpret_cast<const unsigned long long*>(&sv)));
   d = *reinterpret_cast<float2*>(&dd);
 }
+// r.xy = a.xy * s + c.xy   and   r.xy = a.xy * s   (scalar s broadcast to both halves)
+__device__ __forceinline__ float2 ffma2s(const float2 a, const float s, const float2 c) {
+  unsigned long long r;
+  const float2 sv = make_float2(s, s);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&sv)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fmul2s(const float2 a, const float s) {
+  unsigned long long r;
+  const float2 sv = make_float2(s, s);
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&sv)));
+  return *reinterpret_cast<float2*>(&r);
+}
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
   unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
   asm("fma.rn.f32x2 %0, %1, %2, %0;"

@@ -45,6 +45,7 @@ template <typename T, int NS> struct EqKernelParams {
   T dd[NS];
   T g[NS][LC][2];   // c * A^i, i = 0..LC-1
   T pw[NS][5][4];   // A^(LC * 2^d), d = 0..4
+  T ph[NS][4];      // A^(LC / 2): joins a lane's two half chunks (packed fp32 path)
   T gain;
   int clip;
 };
@@ -111,12 +112,9 @@ eq_scan_kernel(const __grid_constant__ EqKernelParams<T, NS> p, const T* __restr
     if (n_tiles > 0) stage_in(0, 0);
     for (long long t = 0; t < n_tiles; ++t) {
       const int st = static_cast<int>(t & 1);
-      if (t + 1 < n_tiles) {
-        stage_in(t + 1, st ^ 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
+      if (t + 1 < n_tiles) stage_in(t + 1, st ^ 1);
+      else cp_async_commit();   // empty group keeps the wait depth uniform
+      cp_async_wait<1>();
       __syncwarp();
       T* cur = buf + st * STAGE + lane * PITCH;
       T v[LC];
@@ -131,7 +129,64 @@ eq_scan_kernel(const __grid_constant__ EqKernelParams<T, NS> p, const T* __restr
         }
       }
 
-      if constexpr (NS > 0) {
+      if constexpr (NS > 0 && kPlain && sizeof(T) == 4) {
+        // Packed fp32 path: the lane's chunk is run as two half chunks (samples
+        // i and i + LC/2) side by side in the two halves of FFMA2 / FMUL2, with
+        // the section coefficients as the broadcast scalar operand.  Half the
+        // issue slots for the same FMA-pipe work.
+        constexpr int H = LC / 2;
+        float2 xp[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) xp[i] = make_float2(v[i], v[H + i]);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float a00 = p.a[s][0], a01 = p.a[s][1], a10 = p.a[s][2], a11 = p.a[s][3];
+          const float c0 = p.c[s][0], c1 = p.c[s][1];
+          float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < H; ++i) {
+            const float2 xi = xp[i];
+            const float2 ty = ffma2s(q1, c1, xi);
+            const float2 t0 = ffma2s(q1, a01, xi);
+            const float2 y = ffma2s(q0, c0, ty);
+            const float2 n0 = ffma2s(q0, a00, t0);
+            const float2 n1 = ffma2s(q0, a10, fmul2s(q1, a11));
+            xp[i] = y;
+            q0 = n0;
+            q1 = n1;
+          }
+          // end state of the whole lane chunk from zero: fB + A^H fA
+          float f0 = q0.y + fmaf(p.ph[s][0], q0.x, p.ph[s][1] * q1.x);
+          float f1 = q1.y + fmaf(p.ph[s][2], q0.x, p.ph[s][3] * q1.x);
+          if (lane == 0) {
+            const float s0 = carry[s][0], s1 = carry[s][1];
+            f0 += fmaf(p.pw[s][0][0], s0, p.pw[s][0][1] * s1);
+            f1 += fmaf(p.pw[s][0][2], s0, p.pw[s][0][3] * s1);
+          }
+#pragma unroll
+          for (int d = 0; d < 5; ++d) {
+            const float u0 = __shfl_up_sync(0xffffffffu, f0, 1 << d);
+            const float u1 = __shfl_up_sync(0xffffffffu, f1, 1 << d);
+            if (lane >= (1 << d)) {
+              f0 += fmaf(p.pw[s][d][0], u0, p.pw[s][d][1] * u1);
+              f1 += fmaf(p.pw[s][d][2], u0, p.pw[s][d][3] * u1);
+            }
+          }
+          float e0 = __shfl_up_sync(0xffffffffu, f0, 1);
+          float e1 = __shfl_up_sync(0xffffffffu, f1, 1);
+          if (lane == 0) { e0 = carry[s][0]; e1 = carry[s][1]; }
+          carry[s][0] = __shfl_sync(0xffffffffu, f0, 31);
+          carry[s][1] = __shfl_sync(0xffffffffu, f1, 31);
+          // true initial states: first half chunk e, second half chunk A^H e + fA
+          const float b0 = q0.x + fmaf(p.ph[s][0], e0, p.ph[s][1] * e1);
+          const float b1 = q1.x + fmaf(p.ph[s][2], e0, p.ph[s][3] * e1);
+          const float2 E0 = make_float2(e0, b0), E1 = make_float2(e1, b1);
+#pragma unroll
+          for (int i = 0; i < H; ++i) xp[i] = ffma2s(E0, p.g[s][i][0], ffma2s(E1, p.g[s][i][1], xp[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) { v[i] = xp[i].x; v[H + i] = xp[i].y; }
+      } else if constexpr (NS > 0) {
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const T a00 = p.a[s][0], a01 = p.a[s][1], a10 = p.a[s][2], a11 = p.a[s][3];
@@ -260,6 +315,11 @@ static void fill_params(EqKernelParams<T, NS>& kp, const Section* sec, bool plai
       double m[4];
       mat2_power(S.a, static_cast<long long>(LC) << d, m);
       for (int i = 0; i < 4; ++i) kp.pw[s][d][i] = static_cast<T>(m[i]);
+    }
+    {
+      double m[4];
+      mat2_power(S.a, LC / 2, m);
+      for (int i = 0; i < 4; ++i) kp.ph[s][i] = static_cast<T>(m[i]);
     }
   }
   kp.gain = static_cast<T>(gain);
