@@ -22,6 +22,7 @@
 // Roofline: 2*sizeof(T) algorithmic bytes per sample; ~8 FMA per section per
 // sample (6 zero-state + 2 correction), i.e. ~50 FMA/sample for six sections.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -129,64 +130,7 @@ eq_scan_kernel(const __grid_constant__ EqKernelParams<T, NS> p, const T* __restr
         }
       }
 
-      if constexpr (NS > 0 && kPlain && sizeof(T) == 4) {
-        // Packed fp32 path: the lane's chunk is run as two half chunks (samples
-        // i and i + LC/2) side by side in the two halves of FFMA2 / FMUL2, with
-        // the section coefficients as the broadcast scalar operand.  Half the
-        // issue slots for the same FMA-pipe work.
-        constexpr int H = LC / 2;
-        float2 xp[H];
-#pragma unroll
-        for (int i = 0; i < H; ++i) xp[i] = make_float2(v[i], v[H + i]);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const float a00 = p.a[s][0], a01 = p.a[s][1], a10 = p.a[s][2], a11 = p.a[s][3];
-          const float c0 = p.c[s][0], c1 = p.c[s][1];
-          float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-            const float2 xi = xp[i];
-            const float2 ty = ffma2s(q1, c1, xi);
-            const float2 t0 = ffma2s(q1, a01, xi);
-            const float2 y = ffma2s(q0, c0, ty);
-            const float2 n0 = ffma2s(q0, a00, t0);
-            const float2 n1 = ffma2s(q0, a10, fmul2s(q1, a11));
-            xp[i] = y;
-            q0 = n0;
-            q1 = n1;
-          }
-          // end state of the whole lane chunk from zero: fB + A^H fA
-          float f0 = q0.y + fmaf(p.ph[s][0], q0.x, p.ph[s][1] * q1.x);
-          float f1 = q1.y + fmaf(p.ph[s][2], q0.x, p.ph[s][3] * q1.x);
-          if (lane == 0) {
-            const float s0 = carry[s][0], s1 = carry[s][1];
-            f0 += fmaf(p.pw[s][0][0], s0, p.pw[s][0][1] * s1);
-            f1 += fmaf(p.pw[s][0][2], s0, p.pw[s][0][3] * s1);
-          }
-#pragma unroll
-          for (int d = 0; d < 5; ++d) {
-            const float u0 = __shfl_up_sync(0xffffffffu, f0, 1 << d);
-            const float u1 = __shfl_up_sync(0xffffffffu, f1, 1 << d);
-            if (lane >= (1 << d)) {
-              f0 += fmaf(p.pw[s][d][0], u0, p.pw[s][d][1] * u1);
-              f1 += fmaf(p.pw[s][d][2], u0, p.pw[s][d][3] * u1);
-            }
-          }
-          float e0 = __shfl_up_sync(0xffffffffu, f0, 1);
-          float e1 = __shfl_up_sync(0xffffffffu, f1, 1);
-          if (lane == 0) { e0 = carry[s][0]; e1 = carry[s][1]; }
-          carry[s][0] = __shfl_sync(0xffffffffu, f0, 31);
-          carry[s][1] = __shfl_sync(0xffffffffu, f1, 31);
-          // true initial states: first half chunk e, second half chunk A^H e + fA
-          const float b0 = q0.x + fmaf(p.ph[s][0], e0, p.ph[s][1] * e1);
-          const float b1 = q1.x + fmaf(p.ph[s][2], e0, p.ph[s][3] * e1);
-          const float2 E0 = make_float2(e0, b0), E1 = make_float2(e1, b1);
-#pragma unroll
-          for (int i = 0; i < H; ++i) xp[i] = ffma2s(E0, p.g[s][i][0], ffma2s(E1, p.g[s][i][1], xp[i]));
-        }
-#pragma unroll
-        for (int i = 0; i < H; ++i) { v[i] = xp[i].x; v[H + i] = xp[i].y; }
-      } else if constexpr (NS > 0) {
+      if constexpr (NS > 0) {
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const T a00 = p.a[s][0], a01 = p.a[s][1], a10 = p.a[s][2], a11 = p.a[s][3];
@@ -274,6 +218,259 @@ eq_scan_kernel(const __grid_constant__ EqKernelParams<T, NS> p, const T* __restr
   }
 }
 
+// ---------------------------------------------------------------------------
+// fp32 fast path: packed arithmetic + several warps per channel.
+//
+// * Packed: the lane's 32-sample chunk runs as two 16-sample halves side by side
+//   in the two lanes of FFMA2/FMUL2 (section coefficients as the broadcast scalar
+//   operand); the 2x2 state algebra of the scan is packed too (a matrix-vector
+//   product is two FFMA2 on column pairs).  Pairs are carried as opaque 64-bit
+//   registers so they stay in aligned register pairs for their whole life.
+// * The section loop is NOT unrolled (runtime section count, one ~450-instruction
+//   body that stays in the instruction cache); per-section constants come from
+//   the kernel-parameter constant bank with a runtime index.
+// * W warps per channel: warp wi takes tiles wi, wi+W, ... of the channel.
+//   Everything except the carry fold is independent of the previous tile, so the
+//   warps run as a wavefront: lane 31 publishes the tile's end state per section
+//   through shared memory (+ an mbarrier when W > 1), the next tile's warp picks
+//   it up just before its own fold.  One channel per CTA keeps the CTAs small
+//   enough to balance 1024 long channels over 148 SMs.
+constexpr int kEqPkLC = 32;
+constexpr int kEqPkPitch = kEqPkLC + 4;
+constexpr int kEqPkMaxNs = 8;
+
+struct EqPackedSection {
+  float a[4];                   // a00 a01 a10 a11
+  float c[2];                   // c / d (direct gain folded into `gain`)
+  float pad[2];
+  float g[kEqPkLC / 2][2];      // (c/d) A^i, i < 16
+  float pwc[5][4];              // A^(32*2^d) as column pairs (p00, p10, p01, p11)
+  float phc[4];                 // A^16, column pairs
+};
+struct EqPackedParams {
+  EqPackedSection sec[kEqPkMaxNs];
+  float gain;
+  int clip;
+  int ns;
+};
+
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk_make(float lo, float hi) {
+  pk2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float pk_lo(pk2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo;
+}
+__device__ __forceinline__ float pk_hi(pk2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return hi;
+}
+// a * s + c   with the scalar s broadcast to both halves
+__device__ __forceinline__ pk2 pk_fma_s(pk2 a, float s, pk2 c) {
+  pk2 r;
+  asm("{\n.reg .b64 sv;\nmov.b64 sv, {%2, %2};\nfma.rn.f32x2 %0, %1, sv, %3;\n}" : "=l"(r) : "l"(a), "f"(s), "l"(c));
+  return r;
+}
+__device__ __forceinline__ pk2 pk_mul_s(pk2 a, float s) {
+  pk2 r;
+  asm("{\n.reg .b64 sv;\nmov.b64 sv, {%2, %2};\nmul.rn.f32x2 %0, %1, sv;\n}" : "=l"(r) : "l"(a), "f"(s));
+  return r;
+}
+// acc += col * s   (in place; call under a predicate for masked updates)
+__device__ __forceinline__ void pk_acc(pk2& acc, pk2 col, float s) {
+  asm("{\n.reg .b64 sv;\nmov.b64 sv, {%2, %2};\nfma.rn.f32x2 %0, %1, sv, %0;\n}" : "+l"(acc) : "l"(col), "f"(s));
+}
+__device__ __forceinline__ float clip_unit_nan(float y) {   // clip to [-1, 1], NaN passes through like np.clip
+  float r;
+  asm("max.NaN.f32 %0, %1, 0fBF800000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(r) : "f"(y));
+  return r;
+}
+
+template <int NS, int W>
+__global__ void __launch_bounds__(W * 32, 24 / W)
+eq_packed_kernel(const __grid_constant__ EqPackedParams p, const float* __restrict__ x, long long x_stride,
+                 float* __restrict__ z, long long z_stride, long long channels, long long n, int aligned) {
+  constexpr int LC = kEqPkLC, H = LC / 2, PITCH = kEqPkPitch;
+  constexpr int TILE = 32 * LC, PIECES = TILE / 4 / 32, STAGE = 32 * PITCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wi = threadIdx.x >> 5;
+  float* buf = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(wi) * 2 * STAGE;
+  float2* cval = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(W) * 2 * STAGE);
+  uint64_t* cbar = reinterpret_cast<uint64_t*>(cval + W * kEqPkMaxNs);   // [warp][section]
+  if constexpr (W > 1) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < W * kEqPkMaxNs; ++i) mbar_init(&cbar[i], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+  }
+  const long long n_tiles = (n + TILE - 1) / TILE;
+  const int prev = (wi + W - 1) % W;                                   // warp that owns tile t-1
+  const long long prev_tiles = n_tiles > prev ? (n_tiles - prev + W - 1) / W : 0;   // carries it publishes per channel
+  uint64_t* wait_bar = cbar + prev * kEqPkMaxNs;
+  const volatile float* wait_val = reinterpret_cast<const volatile float*>(cval + prev * kEqPkMaxNs);
+  uint64_t* pub_bar = cbar + wi * kEqPkMaxNs;
+  volatile float* pub_val = reinterpret_cast<volatile float*>(cval + wi * kEqPkMaxNs);
+  // lane's 16-byte pieces of a tile: element 4*lane + 128*k -> chunk lane/8 + 4k, offset (4*lane)%32
+  const int sm_off = (lane >> 3) * PITCH + ((4 * lane) & 31);
+
+  long long ch_iter = 0;
+  for (long long ch = blockIdx.x; ch < channels; ch += gridDim.x, ++ch_iter) {
+    const float* xc = x + ch * x_stride;
+    float* zc = z + ch * z_stride;
+    if constexpr (W > 1) __syncthreads();   // all carries of the previous channel are consumed
+
+    auto stage_in = [&](long long t, int st) {
+      float* dst = buf + st * STAGE;
+      const long long base = t * TILE;
+      if (aligned && base + TILE <= n) {
+        const float* src = xc + base + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < PIECES; ++k) cp_async16(dst + sm_off + k * 4 * PITCH, src + 128 * k, 16);
+      } else if (aligned) {
+#pragma unroll 1
+        for (int k = 0; k < PIECES; ++k) {
+          const long long gi = base + 4 * lane + 128 * k;
+          const long long rem = (n - gi) * 4;
+          const int nbytes = rem >= 16 ? 16 : (rem > 0 ? static_cast<int>(rem) : 0);
+          cp_async16(dst + sm_off + k * 4 * PITCH, nbytes > 0 ? xc + gi : xc, nbytes);
+        }
+      } else {
+        for (int e = lane; e < TILE; e += 32) {
+          const long long gi = base + e;
+          dst[(e / LC) * PITCH + (e % LC)] = gi < n ? xc[gi] : 0.f;
+        }
+      }
+      cp_async_commit();
+    };
+
+    if (wi < n_tiles) stage_in(wi, 0);
+    int it = 0;
+    for (long long t = wi; t < n_tiles; t += W, ++it) {
+      const int st = it & 1;
+      if (t + W < n_tiles) stage_in(t + W, st ^ 1);
+      else cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      float* cur = buf + st * STAGE + lane * PITCH;
+      pk2 xp[H];
+#pragma unroll
+      for (int i = 0; i < H; i += 4) {
+        const float4 lo = *reinterpret_cast<const float4*>(cur + i);
+        const float4 hi = *reinterpret_cast<const float4*>(cur + H + i);
+        xp[i] = pk_make(lo.x, hi.x); xp[i + 1] = pk_make(lo.y, hi.y);
+        xp[i + 2] = pk_make(lo.z, hi.z); xp[i + 3] = pk_make(lo.w, hi.w);
+      }
+      // parity of the mbarrier phase that carries tile t-1's end states
+      const uint32_t need = static_cast<uint32_t>((ch_iter * prev_tiles + (t - 1 - prev) / W) & 1);
+      const bool first_tile = (t == 0);
+
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const EqPackedSection& q = p.sec[s];
+        const float a00 = q.a[0], a01 = q.a[1], a10 = q.a[2], a11 = q.a[3];
+        const float c0 = q.c[0], c1 = q.c[1];
+        pk2 q0 = 0ull, q1 = 0ull;
+        // 1. zero-state pass over both half chunks
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const pk2 xi = xp[i];
+          const pk2 ty = pk_fma_s(q1, c1, xi);
+          const pk2 t0 = pk_fma_s(q1, a01, xi);
+          const pk2 y = pk_fma_s(q0, c0, ty);
+          const pk2 n0 = pk_fma_s(q0, a00, t0);
+          const pk2 n1 = pk_fma_s(q0, a10, pk_mul_s(q1, a11));
+          xp[i] = y;
+          q0 = n0;
+          q1 = n1;
+        }
+        const pk2 ph0 = pk_make(q.phc[0], q.phc[1]), ph1 = pk_make(q.phc[2], q.phc[3]);
+        const float fA0 = pk_lo(q0), fA1 = pk_lo(q1);
+        pk2 F = pk_make(pk_hi(q0), pk_hi(q1));               // fB
+        pk_acc(F, ph0, fA0);                                 // lane chunk end state from zero: fB + A^16 fA
+        pk_acc(F, ph1, fA1);
+        // 2. carry-in of the tile (end state of tile t-1), folded into lane 0
+        float S0 = 0.f, S1 = 0.f;
+        if (!first_tile) {                                   // warp-uniform
+          if constexpr (W > 1) mbar_spin(&wait_bar[s], need);
+          S0 = wait_val[2 * s];
+          S1 = wait_val[2 * s + 1];
+        }
+        if (lane == 0) {
+          pk_acc(F, pk_make(q.pwc[0][0], q.pwc[0][1]), S0);
+          pk_acc(F, pk_make(q.pwc[0][2], q.pwc[0][3]), S1);
+        }
+        // 3. Kogge-Stone prefix composition across the warp
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+          const float ux = __shfl_up_sync(0xffffffffu, pk_lo(F), 1 << d);
+          const float uy = __shfl_up_sync(0xffffffffu, pk_hi(F), 1 << d);
+          if (lane >= (1 << d)) {
+            pk_acc(F, pk_make(q.pwc[d][0], q.pwc[d][1]), ux);
+            pk_acc(F, pk_make(q.pwc[d][2], q.pwc[d][3]), uy);
+          }
+        }
+        float E0s = __shfl_up_sync(0xffffffffu, pk_lo(F), 1);
+        float E1s = __shfl_up_sync(0xffffffffu, pk_hi(F), 1);
+        if (lane == 0) { E0s = S0; E1s = S1; }
+        __syncwarp();                                        // every lane has read the old carry slot
+        if (lane == 31) {
+          pub_val[2 * s] = pk_lo(F);
+          pub_val[2 * s + 1] = pk_hi(F);
+          if constexpr (W > 1) mbar_arrive(&pub_bar[s]);     // release: the next tile's warp may fold
+        }
+        __syncwarp();
+        // 4. correction with the true initial states (second half chunk: A^16 E + fA)
+        pk2 EB = pk_make(fA0, fA1);
+        pk_acc(EB, ph0, E0s);
+        pk_acc(EB, ph1, E1s);
+        const pk2 E0 = pk_make(E0s, pk_lo(EB)), E1 = pk_make(E1s, pk_hi(EB));
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          pk_acc(xp[i], E1, q.g[i][1]);
+          pk_acc(xp[i], E0, q.g[i][0]);
+        }
+      }
+
+      // gain, clip (dsp_core.py:254), back through shared memory for coalesced stores
+      float ox[H], oy[H];
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const pk2 v = pk_mul_s(xp[i], p.gain);
+        ox[i] = pk_lo(v);
+        oy[i] = pk_hi(v);
+        if (p.clip) { ox[i] = clip_unit_nan(ox[i]); oy[i] = clip_unit_nan(oy[i]); }
+      }
+#pragma unroll
+      for (int i = 0; i < H; i += 4) {
+        *reinterpret_cast<float4*>(cur + i) = make_float4(ox[i], ox[i + 1], ox[i + 2], ox[i + 3]);
+        *reinterpret_cast<float4*>(cur + H + i) = make_float4(oy[i], oy[i + 1], oy[i + 2], oy[i + 3]);
+      }
+      __syncwarp();
+      const float* out = buf + st * STAGE;
+      const long long base = t * TILE;
+      if (aligned && base + TILE <= n) {
+        float* dstg = zc + base + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < PIECES; ++k)
+          *reinterpret_cast<float4*>(dstg + 128 * k) = *reinterpret_cast<const float4*>(out + sm_off + k * 4 * PITCH);
+      } else {
+        for (int e = lane; e < TILE; e += 32) {
+          const long long gi = base + e;
+          if (gi < n) zc[gi] = out[(e / LC) * PITCH + (e % LC)];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ---- plan ------------------------------------------------------------------
 }  // namespace dspb200
 
@@ -351,6 +548,79 @@ static int launch_pass(const Section* sec, bool clip, const T* x, int64_t xs, T*
   return after_launch("eq_scan_kernel");
 }
 
+template <int NS, int W>
+static int launch_packed(const EqPackedParams& kp, const float* x, int64_t xs, float* z, int64_t zs,
+                         int64_t channels, int64_t n, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(W) * 2 * 32 * kEqPkPitch * sizeof(float) +
+                      static_cast<size_t>(W) * kEqPkMaxNs * (sizeof(float2) + sizeof(uint64_t));
+  auto kern = eq_packed_kernel<NS, W>;
+  DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(z) % 16 == 0) &&
+                       (xs % 4 == 0) && (zs % 4 == 0);
+  const int64_t max_ctas = static_cast<int64_t>(sm_count()) * (24 / W);
+  const int grid = static_cast<int>(channels < max_ctas ? channels : max_ctas);
+  kern<<<grid, W * 32, smem, stream>>>(kp, x, xs, z, zs, channels, n, aligned ? 1 : 0);
+  return after_launch("eq_packed_kernel");
+}
+
+static int dispatch_packed(int ns, const Section* sec, bool clip, const float* x, int64_t xs, float* z, int64_t zs,
+                           int64_t channels, int64_t n, cudaStream_t stream) {
+  EqPackedParams kp;
+  memset(&kp, 0, sizeof(kp));
+  double gain = 1.0;
+  for (int s = 0; s < ns; ++s) {
+    const Section& S = sec[s];
+    EqPackedSection& q = kp.sec[s];
+    gain *= S.d;
+    const double c0 = S.c[0] / S.d, c1 = S.c[1] / S.d;
+    for (int i = 0; i < 4; ++i) q.a[i] = static_cast<float>(S.a[i]);
+    q.c[0] = static_cast<float>(c0);
+    q.c[1] = static_cast<float>(c1);
+    for (int i = 0; i < kEqPkLC / 2; ++i) {
+      double m[4];
+      mat2_power(S.a, i, m);
+      q.g[i][0] = static_cast<float>(c0 * m[0] + c1 * m[2]);
+      q.g[i][1] = static_cast<float>(c0 * m[1] + c1 * m[3]);
+    }
+    auto cols = [](const double m[4], float out[4]) {
+      out[0] = static_cast<float>(m[0]); out[1] = static_cast<float>(m[2]);
+      out[2] = static_cast<float>(m[1]); out[3] = static_cast<float>(m[3]);
+    };
+    for (int d = 0; d < 5; ++d) {
+      double m[4];
+      mat2_power(S.a, static_cast<long long>(kEqPkLC) << d, m);
+      cols(m, q.pwc[d]);
+    }
+    double m[4];
+    mat2_power(S.a, kEqPkLC / 2, m);
+    cols(m, q.phc);
+  }
+  kp.gain = static_cast<float>(gain);
+  kp.clip = clip ? 1 : 0;
+  kp.ns = ns;
+  // warps per channel: as few as still fill the machine (24 warps per SM)
+  const int64_t resident = static_cast<int64_t>(sm_count()) * 24;
+  int w = 1;
+  if (const char* e = getenv("DSPB200_EQ_WARPS_PER_CHANNEL")) w = atoi(e);
+  else if (n > 4 * 1024) {
+    // largest W that (nearly) fits one wave of resident warps; a 20 % overshoot
+    // measured faster than dropping to the next smaller W
+    w = static_cast<int>((resident * 6 / 5) / (channels > 0 ? channels : 1));
+    w = w < 1 ? 1 : (w > 4 ? 4 : w);
+  }
+#define DSP_EQ_PK(NSV)                                                                 \
+  case NSV:                                                                            \
+    if (w >= 4) return launch_packed<NSV, 4>(kp, x, xs, z, zs, channels, n, stream);   \
+    if (w == 3) return launch_packed<NSV, 3>(kp, x, xs, z, zs, channels, n, stream);   \
+    if (w == 2) return launch_packed<NSV, 2>(kp, x, xs, z, zs, channels, n, stream);   \
+    return launch_packed<NSV, 1>(kp, x, xs, z, zs, channels, n, stream);
+  switch (ns) {
+    DSP_EQ_PK(1) DSP_EQ_PK(2) DSP_EQ_PK(3) DSP_EQ_PK(4) DSP_EQ_PK(5) DSP_EQ_PK(6) DSP_EQ_PK(7) DSP_EQ_PK(8)
+    default: return fail(DSPB200_ERR_INVALID, "internal: bad section count %d", ns);
+  }
+#undef DSP_EQ_PK
+}
+
 template <typename T, bool kPlain>
 static int dispatch_ns(int ns, const Section* sec, bool clip, const T* x, int64_t xs, T* z, int64_t zs,
                        int64_t channels, int64_t n, cudaStream_t stream) {
@@ -390,7 +660,10 @@ int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs
     for (int s = 0; s < ns; ++s)
       if (!sec[s].complex_poles || sec[s].d == 0.0 || !std::isfinite(1.0 / sec[s].d)) plain = false;
     const bool clip = last && plan->clip != 0;
-    if (plain)
+    if (plain && sizeof(T) == 4 && getenv("DSPB200_EQ_NO_PACKED") == nullptr)
+      DSP_TRY(dispatch_packed(ns, sec, clip, reinterpret_cast<const float*>(src), src_stride,
+                              reinterpret_cast<float*>(z), zs, channels, n, stream));
+    else if (plain)
       DSP_TRY((dispatch_ns<T, true>(ns, sec, clip, src, src_stride, z, zs, channels, n, stream)));
     else
       DSP_TRY((dispatch_ns<T, false>(ns, sec, clip, src, src_stride, z, zs, channels, n, stream)));
