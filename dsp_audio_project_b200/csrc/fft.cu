@@ -28,6 +28,7 @@
 // Roofline (per frame of N real samples): N*sizeof(T) bytes read +
 // (N/2+1)*sizeof(T) written; ~2.5 N log2 N flop.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -54,6 +55,23 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
   r.x = a.x * b.x - a.y * b.y;
   r.y = a.x * b.y + a.y * b.x;
   return r;
+}
+// float2 overloads: one complex number = one packed fp32 pair (FADD2 / FMUL2 / FFMA2);
+// ptxas folds the half swaps and sign flips of -i*z and of the complex product
+// into the instructions' operand modifiers.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {   // a * b = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+  const float2 bs = make_float2(-b.y, b.x);
+  return ffma2s(bs, a.y, fmul2s(b, a.x));
 }
 template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
 template <typename C> __device__ __forceinline__ C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
@@ -280,6 +298,189 @@ fft_stockham_kernel(const FftArgs<T> a) {
       for (int k = t; k < m; k += blockDim.x) o[k] = s[padded(k)];
     }
     // the __syncthreads at the top of the next item protects s
+  }
+}
+
+// ---- compile-time sized variant ---------------------------------------------
+// For the sizes that matter (n_fft 1024..16384 on chip, 2^16 split 4 x 8192) the
+// radix plan, strides and padded shared-memory offsets are compile-time, so the
+// address arithmetic folds into immediates.
+template <int M> struct CtPlan;
+template <> struct CtPlan<512>  { static constexpr int NP = 3; static constexpr int R[4] = {2, 16, 16, 1}; };
+template <> struct CtPlan<1024> { static constexpr int NP = 3; static constexpr int R[4] = {4, 16, 16, 1}; };
+template <> struct CtPlan<2048> { static constexpr int NP = 3; static constexpr int R[4] = {8, 16, 16, 1}; };
+template <> struct CtPlan<4096> { static constexpr int NP = 3; static constexpr int R[4] = {16, 16, 16, 1}; };
+template <> struct CtPlan<8192> { static constexpr int NP = 4; static constexpr int R[4] = {2, 16, 16, 16}; };
+
+template <typename T, int M, int R, int NS>
+__device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
+                                        const typename Cpx<T>::type* __restrict__ tw, const int t) {
+  typedef typename Cpx<T>::type C;
+  constexpr int Q = M / 16, B = 16 / R;
+  C v[16];
+  gather_butterflies<T, R>(v, tmp);
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    const int j = t + b * Q;
+    const int k = j & (NS - 1);
+    C* w = v + b * R;
+    if constexpr (NS > 1) {
+      const C* row = tw + k * kTwPitch;
+      C wv[R];
+#pragma unroll
+      for (int r = 1; r < R; ++r) wv[r] = row[r];
+#pragma unroll
+      for (int r = 1; r < R; ++r) w[r] = cmul(w[r], wv[r]);
+    }
+    Dft<T, R>::run(w);
+    const int base = (j - k) * R + k;
+    C* sp = s + base + (base >> kPadShift);           // padded(base + r*NS) = this + static offset
+#pragma unroll
+    for (int r = 0; r < R; ++r) sp[r * NS + ((r * NS) >> kPadShift)] = w[r];
+  }
+}
+
+template <typename T, int M, int P, int NS>
+__device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
+                                          const typename Cpx<T>::type* tw, const int* tw_offset, const int t) {
+  typedef typename Cpx<T>::type C;
+  if constexpr (P < CtPlan<M>::NP) {
+    constexpr int R = CtPlan<M>::R[P];
+    constexpr int Q = M / 16;
+    if constexpr (P > 0) {
+      const C* lp = s + t + (t >> kPadShift);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) tmp[u] = lp[u * (Q + Q / 16)];
+      __syncthreads();
+    }
+    ct_pass<T, M, R, NS>(tmp, s, tw + tw_offset[P], t);
+    __syncthreads();
+    ct_passes<T, M, P + 1, NS * R>(tmp, s, tw, tw_offset, t);
+  }
+}
+
+template <typename T, int M> struct CtBounds {
+  static constexpr int Q = M / 16;
+  static constexpr int kMinBlocks = sizeof(T) == 4 ? (640 / Q > 0 ? (640 / Q > 16 ? 16 : 640 / Q) : 1)
+                                                   : (256 / Q > 0 ? (256 / Q > 8 ? 8 : 256 / Q) : 1);
+};
+
+template <typename T> __device__ __forceinline__ T mag_sqrt(T v) { return sqrt(v); }
+template <> __device__ __forceinline__ float mag_sqrt<float>(float v) {   // MUFU.SQRT: ~1 ulp, no slow path
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+template <typename T, int MODE, int M, bool kTwSmem>
+__global__ void __launch_bounds__(M / 16, (CtBounds<T, M>::kMinBlocks))
+fft_fixed_kernel(const FftArgs<T> a) {
+  typedef typename Cpx<T>::type C;
+  constexpr int Q = M / 16;
+  constexpr bool kReal = (MODE == 0 || MODE == 1);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  const int t = threadIdx.x;
+  C* stw = s + padded(M) + 1;
+  if constexpr (kTwSmem) {
+    for (int i = t; i < a.tw_total; i += Q) stw[i] = a.tw_pass[i];
+    __syncthreads();
+  }
+  const C* tw = kTwSmem ? stw : a.tw_pass;
+  // MODE 0 keeps the real-split twiddles W_2M^k, k <= M/2, in shared memory as well
+  const C* twp = a.tw_post;
+  if constexpr (MODE == 0 && kTwSmem) {
+    C* sp = stw + a.tw_total;
+    for (int i = t; i <= M / 2; i += Q) sp[i] = a.tw_post[i];
+    twp = sp;
+    __syncthreads();
+  }
+
+  // raw operands of one item, all 16 loads in flight (no window yet)
+  auto fetch = [&](long long item, C* tmp) {
+    const long long f = item / a.r_top;
+    const int rho = static_cast<int>(item - f * a.r_top);
+    if constexpr (kReal) {
+      const long long c = f / a.n_frames;
+      const long long fr = f - c * a.n_frames;
+      const T* xrow = a.x + c * a.x_stride;
+      const long long fstart = a.offset + fr * a.hop;
+      const bool fast = (fstart + 2LL * a.nc <= a.n_valid) &&
+                        (((reinterpret_cast<uintptr_t>(xrow + fstart)) % (2 * sizeof(T))) == 0);
+      if (fast) {
+        const C* xp = reinterpret_cast<const C*>(xrow + fstart) + static_cast<long long>(a.r_top) * t + rho;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (u * Q)];
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const long long s0 = fstart + 2 * (static_cast<long long>(a.r_top) * (t + u * Q) + rho);
+          tmp[u].x = s0 < a.n_valid ? xrow[s0] : T(0);
+          tmp[u].y = s0 + 1 < a.n_valid ? xrow[s0 + 1] : T(0);
+        }
+      }
+    } else {
+      const C* xp = reinterpret_cast<const C*>(a.x) + f * a.nc + static_cast<long long>(a.r_top) * t + rho;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (u * Q)];
+    }
+  };
+
+  C tmp[16];
+  if (blockIdx.x < a.n_items) fetch(blockIdx.x, tmp);
+  for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const long long f = item / a.r_top;
+    const int rho = static_cast<int>(item - f * a.r_top);
+    long long c = 0, fr = 0;
+    if constexpr (kReal) {
+      c = f / a.n_frames;
+      fr = f - c * a.n_frames;
+      if (a.window) {
+        const C* wp = reinterpret_cast<const C*>(a.window) + static_cast<long long>(a.r_top) * t + rho;
+        C wv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) wv[u] = wp[static_cast<long long>(a.r_top) * (u * Q)];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { tmp[u].x *= wv[u].x; tmp[u].y *= wv[u].y; }
+      }
+    }
+    __syncthreads();   // previous item's readers are done with s
+    ct_passes<T, M, 0, 1>(tmp, s, tw, a.tw_offset, t);
+    // the next item's loads fly while this item's epilogue reads shared memory
+    if (item + gridDim.x < a.n_items) fetch(item + gridDim.x, tmp);
+    if constexpr (MODE == 0) {
+      T* mg = a.mag + c * a.mag_channel_stride + fr * a.mag_frame_stride;
+      constexpr int NC = M;   // r_top == 1
+      const C* lp = s + t + (t >> kPadShift);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {          // k = t + i*Q covers 0 .. NC/2 - 1
+        const int k = t + i * Q;
+        const C A = lp[i * (Q + Q / 16)];
+        const int kb = (NC - k) & (NC - 1);
+        const C Bc = cconj(s[kb + (kb >> kPadShift)]);
+        C xe, xo;
+        xe.x = T(0.5) * (A.x + Bc.x); xe.y = T(0.5) * (A.y + Bc.y);
+        xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
+        const C tt = cmul(xo, twp[k]);
+        const C pp = cadd(xe, tt), qq = csub(xe, tt);
+        mg[k] = mag_sqrt(pp.x * pp.x + pp.y * pp.y);
+        mg[NC - k] = mag_sqrt(qq.x * qq.x + qq.y * qq.y);
+      }
+      if (t == 0) {                          // k = NC/2: both magnitudes coincide
+        const C A = s[padded(NC / 2)];
+        mg[NC / 2] = mag_sqrt(A.x * A.x + A.y * A.y);
+      }
+    } else if constexpr (MODE == 2) {
+      C* o = a.out + f * a.nc;
+      const C* lp = s + t + (t >> kPadShift);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) o[t + u * Q] = lp[u * (Q + Q / 16)];
+    } else {
+      C* o = a.out + item * M;
+      const C* lp = s + t + (t >> kPadShift);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) o[t + u * Q] = lp[u * (Q + Q / 16)];
+    }
   }
 }
 
@@ -523,8 +724,36 @@ static int launch_stockham_t(FftArgs<T> a, cudaStream_t stream) {
   return after_launch("fft_stockham_kernel");
 }
 
+template <typename T, int MODE, int M>
+static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
+  typedef typename Cpx<T>::type C;
+  size_t smem = static_cast<size_t>(padded(M) + 1) * sizeof(C);
+  const size_t tw_bytes = static_cast<size_t>(a.tw_total) * sizeof(C);
+  a.tw_in_smem = (tw_bytes > 0 && tw_bytes <= 24 * 1024) ? 1 : 0;
+  if (a.tw_in_smem) smem += tw_bytes + (MODE == 0 ? static_cast<size_t>(M / 2 + 1) * sizeof(C) : 0);
+  auto kern = a.tw_in_smem ? fft_fixed_kernel<T, MODE, M, true> : fft_fixed_kernel<T, MODE, M, false>;
+  DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 1;
+  DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M / 16, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  const int grid = static_cast<int>(a.n_items < cap ? a.n_items : cap);
+  kern<<<grid, M / 16, smem, stream>>>(a);
+  return after_launch("fft_fixed_kernel");
+}
+
 template <typename T, int MODE>
 static int launch_stockham(const FftArgs<T>& a, cudaStream_t stream) {
+  if (getenv("DSPB200_FFT_GENERIC") == nullptr) {
+    switch (a.m) {
+      case 512: return launch_fixed<T, MODE, 512>(a, stream);
+      case 1024: return launch_fixed<T, MODE, 1024>(a, stream);
+      case 2048: return launch_fixed<T, MODE, 2048>(a, stream);
+      case 4096: return launch_fixed<T, MODE, 4096>(a, stream);
+      case 8192: return launch_fixed<T, MODE, 8192>(a, stream);
+      default: break;
+    }
+  }
   const int threads = a.m / 16;
   if (threads <= 128) return launch_stockham_t<T, MODE, 128>(a, stream);
   if (threads <= 256) return launch_stockham_t<T, MODE, 256>(a, stream);
