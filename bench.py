@@ -369,7 +369,7 @@ def run_b200(args):
             "eq": esize * clips * 2 * n_out,
             "fft": esize * clips * n_frames * (N_FFT + bins),
         }
-        kernel_names = {"src": "src_tiled_kernel", "eq": "eq_packed_kernel", "fft": "fft_stockham_kernel"}
+        kernel_names = {"src": "src_tiled_kernel", "eq": "eq_packed_kernel", "fft": "fft_fixed_kernel"}
         kernels = {}
         for k in names:
             gbs = alg_bytes[k] / (per_kernel[k] * 1e-3) / 1e9
