@@ -203,7 +203,7 @@ class ClockSampler:
                     self.max_mhz = int(b)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def stop(self):
         self._stop.set()
