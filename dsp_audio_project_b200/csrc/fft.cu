@@ -73,6 +73,14 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {   // a * b = a.x * 
   const float2 bs = make_float2(-b.y, b.x);
   return ffma2s(bs, a.y, fmul2s(b, a.x));
 }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) {   // elementwise (a.x*b.x, a.y*b.y)
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 pscale(float2 a, float s) { return fmul2s(a, s); }
+__device__ __forceinline__ double2 pscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
 template <typename C> __device__ __forceinline__ C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
 
@@ -378,6 +386,7 @@ fft_fixed_kernel(const FftArgs<T> a) {
   typedef typename Cpx<T>::type C;
   constexpr int Q = M / 16;
   constexpr bool kReal = (MODE == 0 || MODE == 1);
+  constexpr bool kSplit = (MODE == 1 || MODE == 3);   // part of a top-level radix split (r_top > 1)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* s = reinterpret_cast<C*>(smem_raw);
   const int t = threadIdx.x;
@@ -408,21 +417,38 @@ fft_fixed_kernel(const FftArgs<T> a) {
       const bool fast = (fstart + 2LL * a.nc <= a.n_valid) &&
                         (((reinterpret_cast<uintptr_t>(xrow + fstart)) % (2 * sizeof(T))) == 0);
       if (fast) {
-        const C* xp = reinterpret_cast<const C*>(xrow + fstart) + static_cast<long long>(a.r_top) * t + rho;
+        if constexpr (!kSplit) {
+          const C* xp = reinterpret_cast<const C*>(xrow + fstart) + t;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (u * Q)];
+          for (int u = 0; u < 16; ++u) tmp[u] = xp[u * Q];
+        } else {
+          const C* xp = reinterpret_cast<const C*>(xrow + fstart) + static_cast<long long>(a.r_top) * t + rho;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (u * Q)];
+        }
       } else {
+        // tail / misaligned frame: guarded scalar loads, 32-bit index arithmetic relative to the frame
+        const long long left = a.n_valid - fstart;
+        const int rem = left > 0x7fffffff ? 0x7fffffff : (left < 0 ? 0 : static_cast<int>(left));
+        const T* xf = xrow + fstart;
+        const int e0 = 2 * (a.r_top * t + rho), de = 2 * a.r_top * Q;
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const long long s0 = fstart + 2 * (static_cast<long long>(a.r_top) * (t + u * Q) + rho);
-          tmp[u].x = s0 < a.n_valid ? xrow[s0] : T(0);
-          tmp[u].y = s0 + 1 < a.n_valid ? xrow[s0 + 1] : T(0);
+          const int e = e0 + u * de;
+          tmp[u].x = e < rem ? xf[e] : T(0);
+          tmp[u].y = e + 1 < rem ? xf[e + 1] : T(0);
         }
       }
     } else {
-      const C* xp = reinterpret_cast<const C*>(a.x) + f * a.nc + static_cast<long long>(a.r_top) * t + rho;
+      if constexpr (!kSplit) {
+        const C* xp = reinterpret_cast<const C*>(a.x) + f * a.nc + t;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (u * Q)];
+        for (int u = 0; u < 16; ++u) tmp[u] = xp[u * Q];
+      } else {
+        const C* xp = reinterpret_cast<const C*>(a.x) + f * a.nc + static_cast<long long>(a.r_top) * t + rho;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tmp[u] = xp[static_cast<long long>(a.r_top) * (u * Q)];
+      }
     }
   };
 
@@ -436,12 +462,18 @@ fft_fixed_kernel(const FftArgs<T> a) {
       c = f / a.n_frames;
       fr = f - c * a.n_frames;
       if (a.window) {
-        const C* wp = reinterpret_cast<const C*>(a.window) + static_cast<long long>(a.r_top) * t + rho;
         C wv[16];
+        if constexpr (!kSplit) {
+          const C* wp = reinterpret_cast<const C*>(a.window) + t;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) wv[u] = wp[static_cast<long long>(a.r_top) * (u * Q)];
+          for (int u = 0; u < 16; ++u) wv[u] = wp[u * Q];
+        } else {
+          const C* wp = reinterpret_cast<const C*>(a.window) + static_cast<long long>(a.r_top) * t + rho;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) { tmp[u].x *= wv[u].x; tmp[u].y *= wv[u].y; }
+          for (int u = 0; u < 16; ++u) wv[u] = wp[static_cast<long long>(a.r_top) * (u * Q)];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tmp[u] = pmul(tmp[u], wv[u]);
       }
     }
     __syncthreads();   // previous item's readers are done with s
@@ -458,9 +490,8 @@ fft_fixed_kernel(const FftArgs<T> a) {
         const C A = lp[i * (Q + Q / 16)];
         const int kb = (NC - k) & (NC - 1);
         const C Bc = cconj(s[kb + (kb >> kPadShift)]);
-        C xe, xo;
-        xe.x = T(0.5) * (A.x + Bc.x); xe.y = T(0.5) * (A.y + Bc.y);
-        xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
+        const C xe = pscale(cadd(A, Bc), T(0.5));              // (A + conj B) / 2
+        const C xo = pscale(mul_neg_i(csub(A, Bc)), T(0.5));   // -i (A - conj B) / 2
         const C tt = cmul(xo, twp[k]);
         const C pp = cadd(xe, tt), qq = csub(xe, tt);
         mg[k] = mag_sqrt(pp.x * pp.x + pp.y * pp.y);
