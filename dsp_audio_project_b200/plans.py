@@ -100,8 +100,11 @@ class SrcPlan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            _lib.load().dspb200_src_plan_destroy(h)
+        try:
+            if h:
+                _lib.load().dspb200_src_plan_destroy(h)
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def out_len(self, n_in: int) -> int:
         return src_geometry(self.L, self.M, n_in)[2]
@@ -189,8 +192,11 @@ class EqPlan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            _lib.load().dspb200_eq_plan_destroy(h)
+        try:
+            if h:
+                _lib.load().dspb200_eq_plan_destroy(h)
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def describe(self) -> np.ndarray:
         n = C.c_int()
@@ -234,8 +240,11 @@ class FftPlan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            _lib.load().dspb200_fft_plan_destroy(h)
+        try:
+            if h:
+                _lib.load().dspb200_fft_plan_destroy(h)
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def workspace_bytes(self, n_transforms: int) -> int:
         b = C.c_size_t()
