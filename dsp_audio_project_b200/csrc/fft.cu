@@ -83,6 +83,16 @@ __device__ __forceinline__ float2 pscale(float2 a, float s) { return fmul2s(a, s
 __device__ __forceinline__ double2 pscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
 template <typename C> __device__ __forceinline__ C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
+// magnitude (or its dB value) from |X|^2
+__device__ __forceinline__ double finish_mag(double v2, int db) {
+  const double m = sqrt(v2);
+  return db ? 20.0 * log10(m + 1e-12) : m;
+}
+__device__ __forceinline__ float finish_mag(float v2, int db) {
+  float m;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(m) : "f"(v2));      // MUFU.SQRT, ~1 ulp, no slow path
+  return db ? 20.0f * log10f(m + 1e-12f) : m;
+}
 
 // cos/sin(2 pi k / 16), k = 0..7
 __device__ constexpr double kCos16[8] = {1.0, 0.92387953251128673848, 0.70710678118654752440,
@@ -132,6 +142,7 @@ template <typename T> struct FftArgs {
   long long x_stride;
   long long n_valid, offset, hop, n_frames;
   const T* window;         // Hann [2*nc] or nullptr
+  int db;                  // write 20*log10(mag + 1e-12) instead of mag (app.py:207-210)
   // geometry
   int nc;                  // complex points of the whole transform
   int m;                   // complex points of the per-CTA sub-transform (nc = m * r_top)
@@ -297,8 +308,8 @@ fft_stockham_kernel(const FftArgs<T> a) {
         xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
         const C tt = cmul(a.tw_post[k], xo);
         const C p = cadd(xe, tt), q = csub(xe, tt);
-        mg[k] = sqrt(p.x * p.x + p.y * p.y);
-        mg[nc - k] = sqrt(q.x * q.x + q.y * q.y);
+        mg[k] = finish_mag(p.x * p.x + p.y * p.y, a.db);
+        mg[nc - k] = finish_mag(q.x * q.x + q.y * q.y, a.db);
       }
     } else if constexpr (MODE == 2) {
       C* o = a.out + f * a.nc;
@@ -498,12 +509,12 @@ fft_fixed_kernel(const FftArgs<T> a) {
         const C xo = pscale(mul_neg_i(csub(A, Bc)), T(0.5));   // -i (A - conj B) / 2
         const C tt = cmul(xo, twp[k]);
         const C pp = cadd(xe, tt), qq = csub(xe, tt);
-        mg[k] = mag_sqrt(pp.x * pp.x + pp.y * pp.y);
-        mg[NC - k] = mag_sqrt(qq.x * qq.x + qq.y * qq.y);
+        mg[k] = finish_mag(pp.x * pp.x + pp.y * pp.y, a.db);
+        mg[NC - k] = finish_mag(qq.x * qq.x + qq.y * qq.y, a.db);
       }
       if (t == 0) {                          // k = NC/2: both magnitudes coincide
         const C A = s[padded(NC / 2)];
-        mg[NC / 2] = mag_sqrt(A.x * A.x + A.y * A.y);
+        mg[NC / 2] = finish_mag(A.x * A.x + A.y * A.y, a.db);
       }
     } else if constexpr (MODE == 2) {
       C* o = a.out + f * a.nc;
@@ -565,8 +576,8 @@ fft_combine_kernel(const FftArgs<T> a, const typename Cpx<T>::type* __restrict__
         xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
         const C tt = cmul(a.tw_post[idx], xo);
         const C p = cadd(xe, tt), q = csub(xe, tt);
-        mg[idx] = sqrt(p.x * p.x + p.y * p.y);
-        mg[nc - idx] = sqrt(q.x * q.x + q.y * q.y);
+        mg[idx] = finish_mag(p.x * p.x + p.y * p.y, a.db);
+        mg[nc - idx] = finish_mag(q.x * q.x + q.y * q.y, a.db);
       };
 #pragma unroll
       for (int s = 0; s < R; ++s) {
@@ -603,7 +614,7 @@ fft_small_kernel(const FftArgs<T> a, const typename Cpx<T>::type* __restrict__ t
         acc.x += xv * w.x;
         acc.y += xv * w.y;
       }
-      a.mag[c * a.mag_channel_stride + fr * a.mag_frame_stride + k] = sqrt(acc.x * acc.x + acc.y * acc.y);
+      a.mag[c * a.mag_channel_stride + fr * a.mag_frame_stride + k] = finish_mag(acc.x * acc.x + acc.y * acc.y, a.db);
     } else {
       const C* in = reinterpret_cast<const C*>(a.x) + f * n_fft;
       for (int t = 0; t < n_fft; ++t) acc = cadd(acc, cmul(in[t], tw_full[(t * k) & (n_fft - 1)]));
@@ -625,7 +636,7 @@ struct FftSide {
 }  // namespace dspb200
 
 struct dspb200_fft_plan {
-  int n_fft, hann, dtype, device;
+  int n_fft, hann, db, dtype, device;
   dspb200::FftSide real_side, c2c_side;
   void* d_window = nullptr;
   void* d_tw_full = nullptr;   // W_N, for the direct small-size kernel
@@ -838,6 +849,7 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
   FftArgs<T> a{};
   a.x = x; a.x_stride = xs; a.n_valid = n_valid; a.offset = offset; a.hop = hop; a.n_frames = n_frames;
   a.window = static_cast<const T*>(p->d_window);
+  a.db = p->db;
   a.mag = mag; a.mag_frame_stride = mfs; a.mag_channel_stride = mcs;
   const FftSide& s = p->real_side;
   if (p->n_fft < 32) {
@@ -962,7 +974,7 @@ int dspb200_fft_plan_create(int n_fft, int hann, int dtype, dspb200_fft_plan** p
   DSP_TRY(ensure_device());
   dspb200_fft_plan* p = new (std::nothrow) dspb200_fft_plan();
   if (!p) return fail(DSPB200_ERR_ALLOC, "out of host memory");
-  p->n_fft = n_fft; p->hann = hann ? 1 : 0; p->dtype = dtype;
+  p->n_fft = n_fft; p->hann = (hann & DSPB200_FFT_HANN) ? 1 : 0; p->db = (hann & DSPB200_FFT_DB) ? 1 : 0; p->dtype = dtype;
   cudaGetDevice(&p->device);
   int rc = dtype == DSPB200_F32 ? plan_build<float>(p) : plan_build<double>(p);
   if (rc != DSPB200_OK) {

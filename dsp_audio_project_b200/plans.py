@@ -230,12 +230,13 @@ class FftPlan:
     """Radix-2 FFT / Hann magnitude spectrum (replaces fft_diezmado_en_tiempo and
     calcular_espectro_magnitud's arithmetic, dsp_core.py:41-98)."""
 
-    def __init__(self, n_fft: int, dtype=np.float32, hann: bool = True):
+    def __init__(self, n_fft: int, dtype=np.float32, hann: bool = True, db: bool = False):
         self.n_fft = int(n_fft)
         self.bins = self.n_fft // 2 + 1
         self.dtype_id = _dtype_id(dtype)
         self._h = C.c_void_p()
-        check(_lib.load().dspb200_fft_plan_create(self.n_fft, int(bool(hann)), self.dtype_id, C.byref(self._h)))
+        flags = (1 if hann else 0) | (2 if db else 0)   # DSPB200_FFT_HANN | DSPB200_FFT_DB
+        check(_lib.load().dspb200_fft_plan_create(self.n_fft, flags, self.dtype_id, C.byref(self._h)))
         self._ws = None
 
     def __del__(self):
@@ -379,6 +380,52 @@ class Chain:
         check(fn(self.src._h if self.src else None, self.eq._h if self.eq else None, self.fft._h,
                  a.ctypes.data, ch, n_in, z.ctypes.data, mag.ctypes.data))
         return z, mag
+
+
+def to_pcm16(z, out=None):
+    """Playback export of app.py:349-354 on [rows, time] CUDA tensors: nan_to_num,
+    divide by the row peak when it is > 0, * 32767, truncate to int16.
+    Returns (int16 tensor, peaks)."""
+    torch = _torch()
+    dtype_id = _dtype_id(z.dtype)
+    _check_tensor(z, dtype_id, "z")
+    rows, n = z.shape
+    if out is None:
+        out = torch.empty((rows, n), dtype=torch.int16, device=z.device)
+    peaks = torch.empty((rows,), dtype=z.dtype, device=z.device)
+    fn = _lib.load().dspb200_pcm16_run_f32 if dtype_id == F32 else _lib.load().dspb200_pcm16_run_f64
+    with torch.cuda.device(z.device):
+        check(fn(z.data_ptr(), _row_stride(z), peaks.data_ptr(), out.data_ptr(), _row_stride(out), rows, n,
+                 _stream_ptr(z)))
+    return out, peaks
+
+
+def mono_normalize(frames):
+    """Loader front end of dsp_core.py:23-31 on a [clips, frames, channels_in]
+    (or [clips, frames]) CUDA tensor of float64/float32 samples: mono mean in
+    float64, float32 cast, division by the clip peak when it exceeds 1e-6.
+    Returns (float32 [clips, frames], peaks [clips])."""
+    torch = _torch()
+    if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.is_contiguous()):
+        raise TypeError("frames must be a contiguous CUDA tensor")
+    if frames.dim() == 2:
+        frames = frames.unsqueeze(-1)
+    if frames.dim() != 3:
+        raise ValueError("frames must be [clips, frames, channels_in]")
+    clips, n, cin = frames.shape
+    pitch = -(-n // 4) * 4
+    mono = torch.empty((clips, pitch), dtype=torch.float32, device=frames.device)[:, :n]
+    peaks = torch.empty((clips,), dtype=torch.float32, device=frames.device)
+    if frames.dtype == torch.float64:
+        fn = _lib.load().dspb200_mono_normalize_run_f64
+    elif frames.dtype == torch.float32:
+        fn = _lib.load().dspb200_mono_normalize_run_f32
+    else:
+        raise TypeError("frames must be float32 or float64")
+    with torch.cuda.device(frames.device):
+        check(fn(frames.data_ptr(), clips, n, cin, mono.data_ptr(), _row_stride(mono), peaks.data_ptr(),
+                 _stream_ptr(frames)))
+    return mono, peaks
 
 
 @functools.lru_cache(maxsize=32)

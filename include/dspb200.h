@@ -147,10 +147,14 @@ int dspb200_eq_plan_describe(const dspb200_eq_plan* plan, int* n_sections, doubl
                              int capacity_sections);
 
 /* ---- K3: radix-2 FFT (dsp_core.py:41-98) ------------------------------ */
-/* n_fft: power of two, 1 <= n_fft <= DSPB200_FFT_MAX.  hann != 0 applies the
- * reference's symmetric Hann 0.5-0.5cos(2 pi k/(n_fft-1)) (:85-87). */
+/* n_fft: power of two, 1 <= n_fft <= DSPB200_FFT_MAX.  flags: DSPB200_FFT_HANN
+ * applies the reference's symmetric Hann 0.5-0.5cos(2 pi k/(n_fft-1)) (:85-87);
+ * DSPB200_FFT_DB makes the magnitude entry points write 20*log10(mag + 1e-12)
+ * (the app's dB conversion, app.py:207-210) instead of the magnitude. */
 #define DSPB200_FFT_MAX (1 << 17)
-int dspb200_fft_plan_create(int n_fft, int hann, int dtype, dspb200_fft_plan** plan);
+#define DSPB200_FFT_HANN 1
+#define DSPB200_FFT_DB 2
+int dspb200_fft_plan_create(int n_fft, int flags, int dtype, dspb200_fft_plan** plan);
 int dspb200_fft_plan_destroy(dspb200_fft_plan* plan);
 /* Bytes of device workspace a run with this many transforms needs (0 for
  * sizes that fit one CTA's shared memory). */
@@ -208,6 +212,22 @@ int dspb200_chain_host_f32(const dspb200_src_plan* src, const dspb200_eq_plan* e
 int dspb200_chain_host_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq,
                            const dspb200_fft_plan* fft, const double* x, int64_t channels,
                            int64_t n_in, double* z, double* mag);
+
+/* ---- either side of the path (device buffers) -------------- */
+/* Playback export, app.py:349-354: per row nan_to_num, divide by the row peak
+ * when it is > 0, times 32767, truncate to int16.  peaks: rows scratch values
+ * of the input type (receives the peaks). */
+int dspb200_pcm16_run_f32(const float* x, int64_t stride, float* peaks, int16_t* out, int64_t out_stride,
+                          int64_t rows, int64_t n, void* stream);
+int dspb200_pcm16_run_f64(const double* x, int64_t stride, double* peaks, int16_t* out, int64_t out_stride,
+                          int64_t rows, int64_t n, void* stream);
+/* Loader front end, dsp_core.py:23-31: in [clips, frames, channels_in]
+ * interleaved -> mono mean (float64) -> float32 -> divided by the clip's peak
+ * when that is > 1e-6.  mono [clips, frames] float32, peaks [clips] float32. */
+int dspb200_mono_normalize_run_f64(const double* in, int64_t clips, int64_t frames, int channels_in, float* mono,
+                                   int64_t mono_stride, float* peaks, void* stream);
+int dspb200_mono_normalize_run_f32(const float* in, int64_t clips, int64_t frames, int channels_in, float* mono,
+                                   int64_t mono_stride, float* peaks, void* stream);
 
 /* Number of kernels this library has launched on the calling process since
  * load (bench.py's gpu_launches). */

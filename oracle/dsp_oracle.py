@@ -318,6 +318,39 @@ def chain(x, fs, M, L, gains, n_fft=4096):
     return y, z, frame_magnitudes(z, n_fft), fs2
 
 
+# --------------------------------------------------------------------------
+# Either side of the path
+# --------------------------------------------------------------------------
+def load_mono_normalize(frames):
+    """dsp_core.py:23-31 after the file read: stereo -> mono mean (:23-24),
+    float32 (:26), division by the peak when it exceeds 1e-6 (:29-31).
+    `frames` is what soundfile returns: [n] or [n, channels]."""
+    x = np.asarray(frames)
+    if x.ndim > 1:
+        x = x.mean(axis=1)
+    x = x.astype(np.float32)
+    peak = np.max(np.abs(x)) if x.size else np.float32(0)
+    if peak > 1e-6:
+        x = x / peak
+    return x
+
+
+def spectrum_db(mag):
+    """app.py:207-210: 20*log10(mag + 1e-12)."""
+    return 20 * np.log10(np.asarray(mag) + 1e-12)
+
+
+def pcm16_export(z):
+    """app.py:349-354: nan_to_num, divide by the peak when it is > 0, * 32767,
+    truncate to int16.  (Inline code of the Streamlit script, which cannot be
+    imported here: parity for this helper is unpinned.)"""
+    y = np.nan_to_num(np.asarray(z))
+    peak = np.max(np.abs(y)) if y.size else 0
+    if peak > 0:
+        y = y / peak
+    return (y * 32767).astype(np.int16)
+
+
 def rel_err(a, ref) -> float:
     """max|a-ref| / max|ref| (the north star's relative error)."""
     a = np.asarray(a)

@@ -182,6 +182,26 @@ def main():
                         z_sum=np.array([np.sum(z), np.sum(np.abs(z)), np.sum(z * z)]),
                         mag4096=mag, f_app=f3, m_app=m3, fs2=np.array(fs2))
 
+    # ---------------- loader front end (dsp_core.py:10-35) ------------------
+    # the real cargar_senal_audio, fed through a stand-in soundfile.read
+    rng = np.random.default_rng(5)
+    loader = {}
+    frames_in = {
+        "stereo": rng.uniform(-0.7, 0.7, (3000, 2)),
+        "mono": rng.uniform(-0.2, 0.2, 2500),
+        "quad": rng.uniform(-1.5, 1.5, (1200, 4)),
+        "tiny": rng.uniform(-1, 1, (500, 2)) * 1e-7,
+        "silence": np.zeros((300, 2)),
+    }
+    import soundfile as sf_stub
+    for name, arr in frames_in.items():
+        sf_stub.read = (lambda a: (lambda _buf: (a, 44100)))(arr)
+        out, fs_l = ref.cargar_senal_audio("ignored")
+        assert fs_l == 44100 and out.dtype == np.float32 and out.shape == arr.shape[:1]
+        loader[f"in_{name}"] = arr
+        loader[f"out_{name}"] = out
+    np.savez_compressed(os.path.join(HERE, "loader.npz"), **loader)
+
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             manifest["files"][name] = os.path.getsize(os.path.join(HERE, name))

@@ -147,3 +147,18 @@ def test_known_answers():
     x = np.random.default_rng(0).normal(size=256)
     X = o.fft_dit_recursive(x)
     assert abs(np.sum(np.abs(X) ** 2) / 256 - np.sum(x * x)) < 1e-9
+
+
+def test_loader_front_end_matches_reference():
+    from conftest import load_golden
+    g = load_golden("loader.npz")
+    for name in ("stereo", "mono", "quad", "tiny", "silence"):
+        out = o.load_mono_normalize(g[f"in_{name}"])
+        assert out.dtype == np.float32 and np.array_equal(out, g[f"out_{name}"]), name
+
+
+def test_export_helpers_known_answers():
+    z = np.array([0.5, -1.0, np.nan, 0.25])
+    assert np.array_equal(o.pcm16_export(z), np.array([16383, -32767, 0, 8191], dtype=np.int16))
+    assert np.array_equal(o.pcm16_export(np.zeros(3)), np.zeros(3, dtype=np.int16))
+    assert abs(o.spectrum_db(np.array([1.0]))[0]) < 1e-9 and abs(o.spectrum_db(np.array([0.0]))[0] + 240) < 1e-9

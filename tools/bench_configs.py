@@ -87,6 +87,22 @@ def main():
         report(f"FFT 4096 {ch}x2^20 {tag}", ms, x.numel(), es * (x.numel() + mag2.numel()))
         del x, mag, mag2
         torch.cuda.empty_cache()
+        # either side of the path: int16 export and dB spectra
+        z = torch.rand((1024, 480000), generator=gen, device=dev, dtype=tdt) * 2 - 1
+        out16, _ = pkg.to_pcm16(z)
+        ms = timeit(lambda: pkg.to_pcm16(z, out=out16), args.reps)
+        report(f"pcm16 export 1024x480000 {tag} (peak pass + quantise pass)", ms, z.numel(), (2 * es + 2) * z.numel())
+        fdb = pkg.FftPlan(4096, ndt, hann=True, db=True)
+        mdb = fdb.magnitudes(z)
+        ms = timeit(lambda: fdb.magnitudes(z, out=mdb), args.reps)
+        report(f"FFT 4096 dB output 1024x480000 {tag}", ms, z.numel() // 4096 * 4096, es * (mdb.numel() * 4096 // 2049 + mdb.numel()))
+        del z, out16, mdb
+    # loader front end: 1024 stereo float64 clips of 10 s
+    fr = torch.rand((1024, 441000, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5
+    mono, _ = pkg.mono_normalize(fr)
+    ms = timeit(lambda: pkg.mono_normalize(fr), args.reps)
+    report("loader front end 1024x441000 stereo f64 -> mono f32 (mean pass + normalise pass)", ms, mono.numel(),
+           fr.numel() * 8 + 3 * mono.numel() * 4)
 
 
 if __name__ == "__main__":
