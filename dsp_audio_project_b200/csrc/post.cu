@@ -40,23 +40,56 @@ template <typename T> __device__ __forceinline__ T warp_max(T v) {
   return v;
 }
 
+// Four consecutive elements per thread and iteration: one 16-byte (fp32) or two
+// 16-byte (fp64) loads when the row is 16-byte aligned, scalar loads otherwise.
+template <typename T, bool kVec> struct Quad;
+template <bool kVec> struct Quad<float, kVec> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    if (kVec) {
+      const float4 q = *reinterpret_cast<const float4*>(p);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+    }
+  }
+};
+template <bool kVec> struct Quad<double, kVec> {
+  static __device__ __forceinline__ void load(const double* p, double (&v)[4]) {
+    if (kVec) {
+      const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+      v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+    }
+  }
+};
+
 // peaks[row] = max |nan_to_num(x[row, :])|   (peaks zeroed by the caller)
-template <typename T>
+// grid: (chunks along the row, rows), 256 threads, each chunk a whole number of quads
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(256)
-row_peak_kernel(const T* __restrict__ x, long long stride, long long rows, long long n, int chunks_per_row,
+row_peak_kernel(const T* __restrict__ x, long long stride, long long rows, long long n, long long chunk,
                 T* __restrict__ peaks) {
-  const long long total = rows * chunks_per_row;
-  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-    const long long row = w / chunks_per_row;
-    const int chunk = static_cast<int>(w - row * chunks_per_row);
-    const long long per = (n + chunks_per_row - 1) / chunks_per_row;
-    const long long lo = chunk * per;
-    const long long hi = lo + per < n ? lo + per : n;
+  for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
     const T* xr = x + row * stride;
+    const long long lo = static_cast<long long>(blockIdx.x) * chunk;
+    const long long hi = lo + chunk < n ? lo + chunk : n;
     T m = T(0);
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      const T v = nan_to_num(xr[i]);
-      const T a = v < T(0) ? -v : v;
+    long long i = lo + 4LL * threadIdx.x;
+#pragma unroll 4
+    for (; i + 3 < hi; i += 4LL * blockDim.x) {
+      T v[4];
+      Quad<T, kVec>::load(xr + i, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const T w = nan_to_num(v[k]);
+        const T a = w < T(0) ? -w : w;
+        m = a > m ? a : m;
+      }
+    }
+    for (; i < hi; ++i) {          // at most one partial quad per chunk (the row tail)
+      const T w = nan_to_num(xr[i]);
+      const T a = w < T(0) ? -w : w;
       m = a > m ? a : m;
     }
     m = warp_max(m);
@@ -65,75 +98,115 @@ row_peak_kernel(const T* __restrict__ x, long long stride, long long rows, long 
 }
 
 // out = (int16) trunc(nan_to_num(x) / peak * 32767)   (no division when peak == 0)   app.py:349-354
-template <typename T>
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(256)
 pcm16_kernel(const T* __restrict__ x, long long stride, const T* __restrict__ peaks, short* __restrict__ out,
-             long long out_stride, long long rows, long long n) {
-  const long long total = rows * n;
-  for (long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; id < total;
-       id += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = id / n;
-    const long long i = id - row * n;
-    T v = nan_to_num(x[row * stride + i]);
+             long long out_stride, long long rows, long long n, long long chunk) {
+  for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
+    const T* xr = x + row * stride;
+    short* orow = out + row * out_stride;
     const T pk = peaks[row];
-    if (pk > T(0)) v = v / pk;
-    const T s = v * T(32767);
-    out[row * out_stride + i] = static_cast<short>(static_cast<int>(s));   // C truncation, as ndarray.astype
+    const bool scale = pk > T(0);
+    const long long lo = static_cast<long long>(blockIdx.x) * chunk;
+    const long long hi = lo + chunk < n ? lo + chunk : n;
+    auto quant = [&](T v) -> short {
+      v = nan_to_num(v);
+      if (scale) v = v / pk;
+      return static_cast<short>(static_cast<int>(v * T(32767)));   // C truncation, as ndarray.astype
+    };
+    long long i = lo + 4LL * threadIdx.x;
+#pragma unroll 4
+    for (; i + 3 < hi; i += 4LL * blockDim.x) {
+      T v[4];
+      Quad<T, kVec>::load(xr + i, v);
+      const short s0 = quant(v[0]), s1 = quant(v[1]), s2 = quant(v[2]), s3 = quant(v[3]);
+      if (kVec) {
+        uint2 pkd;
+        pkd.x = (static_cast<unsigned>(static_cast<unsigned short>(s1)) << 16) | static_cast<unsigned short>(s0);
+        pkd.y = (static_cast<unsigned>(static_cast<unsigned short>(s3)) << 16) | static_cast<unsigned short>(s2);
+        *reinterpret_cast<uint2*>(orow + i) = pkd;
+      } else {
+        orow[i] = s0; orow[i + 1] = s1; orow[i + 2] = s2; orow[i + 3] = s3;
+      }
+    }
+    for (; i < hi; ++i) orow[i] = quant(xr[i]);
   }
 }
 
-// mono[clip, i] = (float) mean_c in[clip, i, c] (mean in float64), and its running peak
-template <typename TI>
+// mono[clip, i] = (float) mean_c in[clip, i, c] (mean in float64) and the clip's running peak.
+// grid: (chunks along the clip, clips)
+template <typename TI, int CIN>
 __global__ void __launch_bounds__(256)
-mono_kernel(const TI* __restrict__ in, long long clips, long long frames, int cin, float* __restrict__ mono,
-            long long mono_stride, float* __restrict__ peaks) {
-  const long long total = clips * frames;
-  float m = 0.f;
-  long long cur_clip = -1;
-  for (long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; id < total;
-       id += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long clip = id / frames;
-    const long long i = id - clip * frames;
-    if (clip != cur_clip) {
-      if (cur_clip >= 0 && m > 0.f) atomic_max_nonneg(peaks + cur_clip, m);
-      cur_clip = clip;
-      m = 0.f;
+mono_kernel(const TI* __restrict__ in, long long clips, long long frames, int cin_rt, float* __restrict__ mono,
+            long long mono_stride, float* __restrict__ peaks, long long chunk) {
+  const int cin = CIN > 0 ? CIN : cin_rt;
+  for (long long clip = blockIdx.y; clip < clips; clip += gridDim.y) {
+    const TI* src = in + clip * frames * cin;
+    float* dst = mono + clip * mono_stride;
+    const long long lo = static_cast<long long>(blockIdx.x) * chunk;
+    const long long hi = lo + chunk < frames ? lo + chunk : frames;
+    float m = 0.f;
+#pragma unroll 4
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      float v;
+      if (CIN == 1) {
+        v = static_cast<float>(src[i]);
+      } else if (CIN == 2 && sizeof(TI) == 8) {
+        const double2 p = *reinterpret_cast<const double2*>(src + 2 * i);     // one 16-byte load per frame
+        v = static_cast<float>((p.x + p.y) / 2.0);
+      } else if (CIN == 2) {
+        const float2 p = *reinterpret_cast<const float2*>(src + 2 * i);
+        v = static_cast<float>((static_cast<double>(p.x) + static_cast<double>(p.y)) / 2.0);
+      } else {
+        double acc = 0.0;      // numpy's mean: float64 accumulation in element order
+        for (int c = 0; c < cin; ++c) acc += static_cast<double>(src[i * cin + c]);
+        v = static_cast<float>(acc / static_cast<double>(cin));
+      }
+      dst[i] = v;
+      const float a = fabsf(v);
+      m = a > m ? a : m;
     }
-    const TI* p = in + (clip * frames + i) * cin;
-    float v;
-    if (cin == 1) {
-      v = static_cast<float>(p[0]);
-    } else {
-      double acc = 0.0;   // numpy's mean: float64 accumulation in element order
-      for (int c = 0; c < cin; ++c) acc += static_cast<double>(p[c]);
-      v = static_cast<float>(acc / static_cast<double>(cin));
-    }
-    mono[clip * mono_stride + i] = v;
-    const float a = fabsf(v);
-    m = a > m ? a : m;     // NaN never wins, like a NaN-free np.max; NaN inputs are outside the loader's contract
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomic_max_nonneg(peaks + clip, m);
   }
-  if (cur_clip >= 0 && m > 0.f) atomic_max_nonneg(peaks + cur_clip, m);
 }
 
+template <bool kVec>
 __global__ void __launch_bounds__(256)
 normalize_kernel(float* __restrict__ mono, long long mono_stride, const float* __restrict__ peaks, long long clips,
-                 long long frames) {
-  const long long total = clips * frames;
-  for (long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; id < total;
-       id += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long clip = id / frames;
-    const long long i = id - clip * frames;
+                 long long frames, long long chunk) {
+  for (long long clip = blockIdx.y; clip < clips; clip += gridDim.y) {
     const float pk = peaks[clip];
-    if (pk > 1e-6f) mono[clip * mono_stride + i] = mono[clip * mono_stride + i] / pk;   // dsp_core.py:29-31
+    if (!(pk > 1e-6f)) continue;                                   // dsp_core.py:29-31
+    float* row = mono + clip * mono_stride;
+    const long long lo = static_cast<long long>(blockIdx.x) * chunk;
+    const long long hi = lo + chunk < frames ? lo + chunk : frames;
+    long long i = lo + 4LL * threadIdx.x;
+#pragma unroll 4
+    for (; i + 3 < hi; i += 4LL * blockDim.x) {
+      if (kVec) {
+        float4 q = *reinterpret_cast<float4*>(row + i);
+        q.x = q.x / pk; q.y = q.y / pk; q.z = q.z / pk; q.w = q.w / pk;
+        *reinterpret_cast<float4*>(row + i) = q;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) row[i + k] = row[i + k] / pk;
+      }
+    }
+    for (; i < hi; ++i) row[i] = row[i] / pk;
   }
 }
 
-static int grid_for(long long work_items, int threads) {
-  long long b = ceil_div(work_items, threads);
-  const long long cap = static_cast<long long>(sm_count()) * 16;
-  if (b > cap) b = cap;
-  if (b < 1) b = 1;
-  return static_cast<int>(b);
+// chunk length (multiple of 1024 elements) and 2-D grid giving ~16 CTAs per SM
+static void tile_rows(long long rows, long long n, long long& chunk, dim3& grid) {
+  const long long want = static_cast<long long>(sm_count()) * 16;
+  long long per_row = ceil_div(want, rows > 0 ? rows : 1);
+  const long long max_chunks = ceil_div(n, 4096);
+  if (per_row > max_chunks) per_row = max_chunks;
+  if (per_row < 1) per_row = 1;
+  chunk = round_up(ceil_div(n, per_row), 1024);
+  per_row = ceil_div(n, chunk);
+  grid = dim3(static_cast<unsigned>(per_row), static_cast<unsigned>(rows < 65535 ? rows : 65535), 1);
 }
 
 template <typename T>
@@ -145,13 +218,17 @@ static int pcm16_run(const T* x, int64_t stride, T* peaks, short* out, int64_t o
   DSP_CHECK(stride >= n && out_stride >= n, "row stride smaller than n");
   DSP_TRY(ensure_device());
   DSP_CUDA(cudaMemsetAsync(peaks, 0, static_cast<size_t>(rows) * sizeof(T), stream));
-  int chunks = static_cast<int>(ceil_div(static_cast<int64_t>(sm_count()) * 8, rows));
-  if (chunks < 1) chunks = 1;
-  const int64_t max_chunks = ceil_div(n, 4096);
-  if (chunks > max_chunks) chunks = static_cast<int>(max_chunks);
-  row_peak_kernel<T><<<grid_for(rows * chunks * 256, 256), 256, 0, stream>>>(x, stride, rows, n, chunks, peaks);
+  long long chunk;
+  dim3 grid;
+  tile_rows(rows, n, chunk, grid);
+  const int vec = 16 / static_cast<int>(sizeof(T));
+  const bool vin = reinterpret_cast<uintptr_t>(x) % 16 == 0 && stride % vec == 0;
+  const bool vout = reinterpret_cast<uintptr_t>(out) % 8 == 0 && out_stride % 4 == 0;
+  if (vin) row_peak_kernel<T, true><<<grid, 256, 0, stream>>>(x, stride, rows, n, chunk, peaks);
+  else row_peak_kernel<T, false><<<grid, 256, 0, stream>>>(x, stride, rows, n, chunk, peaks);
   DSP_TRY(after_launch("row_peak_kernel"));
-  pcm16_kernel<T><<<grid_for(rows * n, 256), 256, 0, stream>>>(x, stride, peaks, out, out_stride, rows, n);
+  if (vin && vout) pcm16_kernel<T, true><<<grid, 256, 0, stream>>>(x, stride, peaks, out, out_stride, rows, n, chunk);
+  else pcm16_kernel<T, false><<<grid, 256, 0, stream>>>(x, stride, peaks, out, out_stride, rows, n, chunk);
   return after_launch("pcm16_kernel");
 }
 
@@ -164,9 +241,17 @@ static int mono_run(const TI* in, int64_t clips, int64_t frames, int cin, float*
   DSP_CHECK(mono_stride >= frames, "mono stride smaller than frames");
   DSP_TRY(ensure_device());
   DSP_CUDA(cudaMemsetAsync(peaks, 0, static_cast<size_t>(clips) * sizeof(float), stream));
-  mono_kernel<TI><<<grid_for(clips * frames, 256), 256, 0, stream>>>(in, clips, frames, cin, mono, mono_stride, peaks);
+  long long chunk;
+  dim3 grid;
+  tile_rows(clips, frames, chunk, grid);
+  const bool pair_ok = reinterpret_cast<uintptr_t>(in) % (2 * sizeof(TI)) == 0;
+  if (cin == 1) mono_kernel<TI, 1><<<grid, 256, 0, stream>>>(in, clips, frames, cin, mono, mono_stride, peaks, chunk);
+  else if (cin == 2 && pair_ok) mono_kernel<TI, 2><<<grid, 256, 0, stream>>>(in, clips, frames, cin, mono, mono_stride, peaks, chunk);
+  else mono_kernel<TI, 0><<<grid, 256, 0, stream>>>(in, clips, frames, cin, mono, mono_stride, peaks, chunk);
   DSP_TRY(after_launch("mono_kernel"));
-  normalize_kernel<<<grid_for(clips * frames, 256), 256, 0, stream>>>(mono, mono_stride, peaks, clips, frames);
+  const bool vec = reinterpret_cast<uintptr_t>(mono) % 16 == 0 && mono_stride % 4 == 0;
+  if (vec) normalize_kernel<true><<<grid, 256, 0, stream>>>(mono, mono_stride, peaks, clips, frames, chunk);
+  else normalize_kernel<false><<<grid, 256, 0, stream>>>(mono, mono_stride, peaks, clips, frames, chunk);
   return after_launch("normalize_kernel");
 }
 
