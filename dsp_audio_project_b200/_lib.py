@@ -66,6 +66,7 @@ SIGNATURES = {
     "dspb200_chain_run_f64": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
     "dspb200_chain_host_f32": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dspb200_chain_host_f64": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "dspb200_host_release": (C.c_int, []),
     "dspb200_pcm16_run_f32": (C.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_pcm16_run_f64": (C.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_mono_normalize_run_f64": (C.c_int, [c_p, c_i64, c_i64, C.c_int, c_p, c_i64, c_p, c_p]),

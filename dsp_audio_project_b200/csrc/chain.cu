@@ -85,6 +85,34 @@ static int chain_run(const dspb200_src_plan* src, const dspb200_eq_plan* eq, con
   return DSPB200_OK;
 }
 
+// Streams and device buffers of the host-form pipeline, kept per calling thread between
+// calls (cudaMalloc/cudaFree and stream creation are milliseconds; a chain call is tens).
+struct HostPipe {
+  static constexpr int kStreams = 3;
+  int device = -1;
+  cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+  void* buf[kStreams][4] = {};          // x, z, mag, workspace
+  size_t cap[kStreams][4] = {};
+  void release() {
+    for (int i = 0; i < kStreams; ++i) {
+      for (int j = 0; j < 4; ++j) { if (buf[i][j]) cudaFree(buf[i][j]); buf[i][j] = nullptr; cap[i][j] = 0; }
+      if (st[i]) cudaStreamDestroy(st[i]);
+      st[i] = nullptr;
+    }
+    device = -1;
+  }
+  cudaError_t ensure(int i, int j, size_t bytes) {
+    if (bytes <= cap[i][j]) return cudaSuccess;
+    if (buf[i][j]) cudaFree(buf[i][j]);
+    buf[i][j] = nullptr; cap[i][j] = 0;
+    cudaError_t e = cudaMalloc(&buf[i][j], bytes);
+    if (e == cudaSuccess) cap[i][j] = bytes;
+    return e;
+  }
+  ~HostPipe() {}   // buffers die with the context; freeing at thread exit could race its teardown
+};
+static thread_local HostPipe g_pipe;
+
 template <typename T>
 static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
                       const T* x, int64_t channels, int64_t n_in, T* z, T* mag) {
@@ -92,7 +120,7 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
   if (channels == 0) return DSPB200_OK;
   DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
   DSP_TRY(ensure_device());
-  int64_t slab = 64;
+  int64_t slab = 32;   // measured: 32-channel slabs pipeline best against PCIe (63 ms vs 65 ms at 64, 68 ms at 128 per 1024-clip wave)
   if (const char* e = getenv("DSPB200_CHAIN_SLAB")) {
     const long v = atol(e);
     if (v > 0) slab = v;
@@ -102,9 +130,16 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
   DSP_TRY(chain_shape<T>(src, fft, slab, n_in, s));
   const int vec = 16 / static_cast<int>(sizeof(T));
   const int64_t xp = round_up(n_in, vec);
-  constexpr int kStreams = 3;
+  constexpr int kStreams = HostPipe::kStreams;
   const int n_streams = static_cast<int>(ceil_div(channels, slab) < kStreams ? ceil_div(channels, slab) : kStreams);
-  cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+  HostPipe& hp = g_pipe;
+  int dev_now = 0;
+  DSP_CUDA(cudaGetDevice(&dev_now));
+  if (hp.device != dev_now) {
+    hp.release();
+    hp.device = dev_now;
+  }
+  cudaStream_t* st = hp.st;
   T* dx[kStreams] = {nullptr, nullptr, nullptr};
   T* dz[kStreams] = {nullptr, nullptr, nullptr};
   T* dm[kStreams] = {nullptr, nullptr, nullptr};
@@ -114,11 +149,15 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
   cudaError_t e = cudaSuccess;
   int rc = DSPB200_OK;
   for (int i = 0; i < n_streams && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&dx[i], static_cast<size_t>(slab) * xp * sizeof(T));
-    if (e == cudaSuccess) e = cudaMalloc(&dz[i], static_cast<size_t>(slab) * s.n_out * sizeof(T));
-    if (e == cudaSuccess && mag_elems && mag) e = cudaMalloc(&dm[i], mag_elems * sizeof(T));
-    if (e == cudaSuccess && ws_bytes) e = cudaMalloc(&dw[i], ws_bytes);
+    if (!st[i]) e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = hp.ensure(i, 0, static_cast<size_t>(slab) * xp * sizeof(T));
+    if (e == cudaSuccess) e = hp.ensure(i, 1, static_cast<size_t>(slab) * s.n_out * sizeof(T));
+    if (e == cudaSuccess && mag_elems && mag) e = hp.ensure(i, 2, mag_elems * sizeof(T));
+    if (e == cudaSuccess && ws_bytes) e = hp.ensure(i, 3, ws_bytes);
+    dx[i] = static_cast<T*>(hp.buf[i][0]);
+    dz[i] = static_cast<T*>(hp.buf[i][1]);
+    dm[i] = (mag_elems && mag) ? static_cast<T*>(hp.buf[i][2]) : nullptr;
+    dw[i] = ws_bytes ? hp.buf[i][3] : nullptr;
   }
   int k = 0;
   for (int64_t c0 = 0; c0 < channels && e == cudaSuccess && rc == DSPB200_OK; c0 += slab, ++k) {
@@ -141,11 +180,10 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
       if (e == cudaSuccess) e = e2;
     }
   }
-  for (int i = 0; i < kStreams; ++i) {
-    cudaFree(dx[i]); cudaFree(dz[i]); cudaFree(dm[i]); cudaFree(dw[i]);
-    if (st[i]) cudaStreamDestroy(st[i]);
+  if (e != cudaSuccess) {
+    hp.release();
+    return fail(DSPB200_ERR_CUDA, "chain host path: %s", cudaGetErrorString(e));
   }
-  if (e != cudaSuccess) return fail(DSPB200_ERR_CUDA, "chain host path: %s", cudaGetErrorString(e));
   return rc;
 }
 
@@ -185,6 +223,11 @@ int dspb200_chain_host_f32(const dspb200_src_plan* src, const dspb200_eq_plan* e
                            const float* x, int64_t channels, int64_t n_in, float* z, float* mag) {
   return chain_host<float>(src, eq, fft, x, channels, n_in, z, mag);
 }
+int dspb200_host_release(void) {
+  g_pipe.release();
+  return DSPB200_OK;
+}
+
 int dspb200_chain_host_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
                            const double* x, int64_t channels, int64_t n_in, double* z, double* mag) {
   return chain_host<double>(src, eq, fft, x, channels, n_in, z, mag);

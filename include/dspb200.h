@@ -213,6 +213,10 @@ int dspb200_chain_host_f64(const dspb200_src_plan* src, const dspb200_eq_plan* e
                            const dspb200_fft_plan* fft, const double* x, int64_t channels,
                            int64_t n_in, double* z, double* mag);
 
+/* The host form keeps its streams and device slabs per calling thread between
+ * calls; this frees the calling thread's. */
+int dspb200_host_release(void);
+
 /* ---- either side of the path (device buffers) -------------- */
 /* Playback export, app.py:349-354: per row nan_to_num, divide by the row peak
  * when it is > 0, times 32767, truncate to int16.  peaks: rows scratch values
