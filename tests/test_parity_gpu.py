@@ -338,6 +338,38 @@ def test_fft_parseval_and_linearity_full_c4_frame_count(pk, torch_cuda):
     assert float((mag[:2].double() - ref).abs().max() / ref.max()) <= TOL_F32_FFT
 
 
+@pytest.mark.parametrize("n_fft", [32768, 65536, 131072])
+def test_fft_long_split_transforms(pk, dc, torch_cuda, n_fft):
+    """Transforms longer than one CTA's shared memory take a top-level radix-2..16
+    split through a workspace; ragged / misaligned / many-frame input against numpy."""
+    torch = torch_cuda
+    rng = np.random.default_rng(n_fft + 1)
+    w = o.hann_symmetric(n_fft)
+    channels, n_frames = 2, 3
+    x = rng.uniform(-1, 1, (channels, n_fft * n_frames + 9))
+    ref = np.abs(np.fft.rfft(x[:, :n_fft * n_frames].reshape(channels, n_frames, n_fft) * w, axis=-1))
+    xz = np.zeros((channels, 3 * n_fft)); xz[:, :n_fft + 7] = x[:, :n_fft + 7]
+    ref2 = np.stack([np.abs(np.fft.rfft(xz[:, 3 + f * (n_fft // 2):3 + f * (n_fft // 2) + n_fft] * w, axis=-1))
+                     for f in range(2)], axis=1)
+    for dt, tol in ((np.float64, TOL_F64), (np.float32, TOL_F32_FFT)):
+        plan = pk.FftPlan(n_fft, dt, hann=True)
+        xt = torch.as_tensor(x.astype(dt), device="cuda")
+        mag = plan.magnitudes(xt).cpu().numpy()
+        assert o.rel_err(mag, ref) <= tol, dt
+        m2 = plan.magnitudes(xt, hop=n_fft // 2, offset=3, n_frames=2, n_valid=n_fft + 7).cpu().numpy()
+        assert o.rel_err(m2, ref2) <= tol, (dt, "ragged")
+    if n_fft == 32768:
+        # many frames: every CTA loops over several transforms
+        gen = torch.Generator(device="cuda").manual_seed(11)
+        xm = torch.rand((700, n_fft), generator=gen, device="cuda") * 2 - 1
+        plan = pk.FftPlan(n_fft, np.float32, hann=False)
+        mag = plan.magnitudes(xm)[:, 0]
+        refm = torch.fft.rfft(xm.double(), dim=-1).abs()
+        assert float((mag.double() - refm).abs().max() / refm.max()) <= TOL_F32_FFT
+        xc = rng.normal(size=n_fft) + 1j * rng.normal(size=n_fft)
+        assert o.rel_err(dc.fft_diezmado_en_tiempo(xc), np.fft.fft(xc)) <= TOL_F64
+
+
 # ---------------------------------------------------------------- chain ----
 def test_chain_c1_golden(dc, pk, golden_chain, torch_cuda):
     torch = torch_cuda

@@ -53,7 +53,18 @@ def report(name, ms, samples, alg_bytes, extra=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="c4: just the 2^16-point FFT case")
     args = ap.parse_args()
+    if args.only == "c4":
+        dev = torch.device("cuda", 0)
+        gen = torch.Generator(device=dev).manual_seed(3)
+        for tdt, ndt, es, tag, ch in ((torch.float32, np.float32, 4, "f32", 512), (torch.float64, np.float64, 8, "f64", 256)):
+            x = torch.rand((ch, 1 << 20), generator=gen, device=dev, dtype=tdt) * 2 - 1
+            fft = pkg.FftPlan(65536, ndt, hann=True)
+            mag = fft.magnitudes(x)
+            ms = timeit(lambda: fft.magnitudes(x, out=mag), args.reps)
+            report(f"C4 slice FFT 2^16 {ch}x2^20 {tag}", ms, x.numel(), es * (x.numel() + mag.numel()))
+        return
     dev = torch.device("cuda", 0)
     gen = torch.Generator(device=dev).manual_seed(1)
     for tdt, ndt, es, tag in ((torch.float32, np.float32, 4, "f32"), (torch.float64, np.float64, 8, "f64")):
