@@ -327,6 +327,8 @@ fft_stockham_kernel(const FftArgs<T> a) {
 // radix plan, strides and padded shared-memory offsets are compile-time, so the
 // address arithmetic folds into immediates.
 template <int M> struct CtPlan;
+template <> struct CtPlan<128>  { static constexpr int NP = 2; static constexpr int R[4] = {8, 16, 1, 1}; };
+template <> struct CtPlan<256>  { static constexpr int NP = 2; static constexpr int R[4] = {16, 16, 1, 1}; };
 template <> struct CtPlan<512>  { static constexpr int NP = 3; static constexpr int R[4] = {2, 16, 16, 1}; };
 template <> struct CtPlan<1024> { static constexpr int NP = 3; static constexpr int R[4] = {4, 16, 16, 1}; };
 template <> struct CtPlan<2048> { static constexpr int NP = 3; static constexpr int R[4] = {8, 16, 16, 1}; };
@@ -369,9 +371,14 @@ __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename C
     constexpr int R = CtPlan<M>::R[P];
     constexpr int Q = M / 16;
     if constexpr (P > 0) {
-      const C* lp = s + t + (t >> kPadShift);
+      if constexpr (Q % 16 == 0) {
+        const C* lp = s + t + (t >> kPadShift);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) tmp[u] = lp[u * (Q + Q / 16)];
+        for (int u = 0; u < 16; ++u) tmp[u] = lp[u * (Q + Q / 16)];
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tmp[u] = s[padded(t + u * Q)];
+      }
       __syncthreads();
     }
     ct_pass<T, M, R, NS>(tmp, s, tw + tw_offset[P], t);
@@ -589,6 +596,142 @@ fft_combine_kernel(const FftArgs<T> a, const typename Cpx<T>::type* __restrict__
   }
 }
 
+// ---- four-step form of long real transforms (2^15 .. 2^18 points, config C4) ----
+// nc = N1 x 128 complex points, z[n1*128 + n2].  Kernel 1 transforms 16 adjacent
+// columns per CTA (N1-point transforms over n1; a warp reads 2 rows x 128 B, so
+// every sector is used once), multiplies by W_nc^(n2 k1) and writes ws[k1][n2].
+// Kernel 2 transforms 32 rows per CTA (128-point transforms over n2): 16 rows k1
+// and their mirror rows N1-k1, which is what the real split needs to turn
+// Z[k1 + N1 k2] / Z[nc - k1 - N1 k2] into |X| with 64-byte coalesced stores.
+constexpr int kFsCols = 128;     // N2
+constexpr int kFsTile = 16;      // columns per CTA (kernel 1), primary rows per CTA (kernel 2)
+
+template <typename T> struct FourStep {
+  typedef typename Cpx<T>::type C;
+  const C* tw_cols; int tw_cols_offset[8];   // N1-point passes
+  const C* tw_rows; int tw_rows_offset[8];   // 128-point passes
+  const C* tw_hi;                            // W_nc^(256 q), q < nc/256
+  const C* tw_lo;                            // W_nc^r, r < 256
+  C* ws;
+};
+
+template <int M> __host__ __device__ constexpr int fs_pitch() { return (M + (M >> kPadShift)) | 1; }
+
+template <typename T, int N1>
+__global__ void __launch_bounds__(N1)
+fft4_cols_kernel(const FftArgs<T> a, const FourStep<T> fs) {
+  typedef typename Cpx<T>::type C;
+  constexpr int Q = N1 / 16, NC = N1 * kFsCols, PITCH = fs_pitch<N1>();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  C* s_hi = s + kFsTile * PITCH;
+  C* s_lo = s_hi + NC / 256;
+  const int t = threadIdx.x;
+  const int c = t % kFsTile, tp = t / kFsTile;
+  for (int i = t; i < NC / 256; i += N1) s_hi[i] = fs.tw_hi[i];
+  for (int i = t; i < 256; i += N1) s_lo[i] = fs.tw_lo[i];
+  constexpr int TILES = kFsCols / kFsTile;
+  const long long fl = blockIdx.x / TILES;
+  const int n2 = static_cast<int>(blockIdx.x - fl * TILES) * kFsTile + c;
+  const long long f = a.first + fl;
+  const long long ch = f / a.n_frames;
+  const long long fr = f - ch * a.n_frames;
+  const long long fstart = a.offset + fr * a.hop;
+  const T* xf = a.x + ch * a.x_stride + fstart;
+  const long long left = a.n_valid - fstart;
+  C tmp[16];
+  if (left >= 2LL * NC && (reinterpret_cast<uintptr_t>(xf) % (2 * sizeof(T))) == 0) {
+    const C* xp = reinterpret_cast<const C*>(xf) + tp * kFsCols + n2;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) tmp[u] = xp[u * Q * kFsCols];
+  } else {
+    const int rem = left > 0x7fffffff ? 0x7fffffff : (left < 0 ? 0 : static_cast<int>(left));
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = 2 * ((tp + u * Q) * kFsCols + n2);
+      tmp[u].x = e < rem ? xf[e] : T(0);
+      tmp[u].y = e + 1 < rem ? xf[e + 1] : T(0);
+    }
+  }
+  if (a.window) {
+    const C* wp = reinterpret_cast<const C*>(a.window) + tp * kFsCols + n2;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) tmp[u] = pmul(tmp[u], wp[u * Q * kFsCols]);
+  }
+  C* sc = s + c * PITCH;
+  ct_passes<T, N1, 0, 1>(tmp, sc, fs.tw_cols, fs.tw_cols_offset, tp);
+  C* o = fs.ws + fl * NC + n2;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int k1 = tp + u * Q;
+    const int q = n2 * k1;
+    const C w = cmul(s_hi[q >> 8], s_lo[q & 255]);
+    o[static_cast<long long>(k1) * kFsCols] = cmul(sc[padded(k1)], w);
+  }
+}
+
+template <typename T, int N1>
+__global__ void __launch_bounds__(256)
+fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
+  typedef typename Cpx<T>::type C;
+  constexpr int M = kFsCols, Q = M / 16, NC = N1 * M, PITCH = fs_pitch<M>();
+  constexpr int G = N1 / 2 / kFsTile;     // groups of 16 primary rows k1 in [1, N1/2]; block G of a frame is row 0
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  const int t = threadIdx.x;
+  const int tp = t % Q, slot = t / Q;     // 32 row slots: 0..15 primary rows, 16..31 their mirrors (ascending)
+  const long long fl = blockIdx.x / (G + 1);
+  const int g = static_cast<int>(blockIdx.x - fl * (G + 1));
+  const long long f = a.first + fl;
+  int row = -1;
+  if (g < G) row = slot < kFsTile ? (kFsTile * g + 1 + slot) : (N1 - kFsTile * g - 2 * kFsTile + slot);
+  else if (slot == 0) row = 0;
+  C tmp[16];
+  if (row >= 0) {
+    const C* wp = fs.ws + fl * NC + static_cast<long long>(row) * M + tp;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) tmp[u] = wp[u * Q];
+  } else {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { tmp[u].x = T(0); tmp[u].y = T(0); }
+  }
+  ct_passes<T, M, 0, 1>(tmp, s + slot * PITCH, fs.tw_rows, fs.tw_rows_offset, tp);
+
+  const long long ch = f / a.n_frames;
+  const long long fr = f - ch * a.n_frames;
+  T* mg = a.mag + ch * a.mag_channel_stride + fr * a.mag_frame_stride;
+  auto emit = [&](const C A, const C Bz, int idx) {      // A = Z[idx], Bz = Z[nc - idx], idx <= nc/2
+    const C Bc = cconj(Bz);
+    C xe, xo;
+    xe.x = T(0.5) * (A.x + Bc.x); xe.y = T(0.5) * (A.y + Bc.y);
+    xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
+    const C tt = cmul(a.tw_post[idx], xo);
+    const C p = cadd(xe, tt), q = csub(xe, tt);
+    mg[idx] = finish_mag(p.x * p.x + p.y * p.y, a.db);
+    mg[NC - idx] = finish_mag(q.x * q.x + q.y * q.y, a.db);
+  };
+  if (g < G) {
+    const int j = t % kFsTile;
+    const int k1 = kFsTile * g + 1 + j;
+    const C* pa = s + j * PITCH;
+    const C* pb = s + (2 * kFsTile - 1 - j) * PITCH;     // row N1 - k1
+#pragma unroll
+    for (int i = 0; i < M / 16; ++i) {
+      const int k2 = t / kFsTile + 16 * i;
+      const C A = pa[padded(k2)];
+      const C Bz = pb[padded(M - 1 - k2)];
+      const int idx = k1 + N1 * k2;
+      if (idx <= NC / 2) {
+        if (2 * k1 != N1 || k2 < M / 2) emit(A, Bz, idx);  // row N1/2 pairs with itself: take each pair once
+      } else if (2 * k1 != N1) {
+        emit(Bz, A, NC - idx);
+      }
+    }
+  } else if (t <= M / 2) {                                 // row 0 pairs with itself, k2 <-> (M - k2) mod M
+    emit(s[padded(t)], s[padded((M - t) & (M - 1))], N1 * t);
+  }
+}
+
 // Direct DFT for tiny transforms (nc < 16): one thread per output bin.
 template <typename T, bool kReal>
 __global__ void __launch_bounds__(128)
@@ -638,6 +781,10 @@ struct FftSide {
 struct dspb200_fft_plan {
   int n_fft, hann, db, dtype, device;
   dspb200::FftSide real_side, c2c_side;
+  dspb200::FftSide fs_cols, fs_rows;   // four-step form of a long real transform: N1-point columns, 128-point rows
+  int fs_n1 = 0;                        // 0: not available for this size / dtype
+  void* d_fs_hi = nullptr;
+  void* d_fs_lo = nullptr;
   void* d_window = nullptr;
   void* d_tw_full = nullptr;   // W_N, for the direct small-size kernel
 };
@@ -720,6 +867,32 @@ static int plan_build(dspb200_fft_plan* p) {
     else if (rc != DSPB200_OK) return rc;
   }
   if (N < 32) DSP_TRY(upload_twiddles<T>(N, N, &p->d_tw_full));
+  {
+    const int nc = N / 2;
+    const int n1 = nc / kFsCols;
+    const int n1_max = sizeof(T) == 4 ? 1024 : 512;      // 16 columns of N1 points must fit shared memory
+    if (p->real_side.r_top > 1 && n1 >= 128 && n1 <= n1_max) {
+      typedef typename Cpx<T>::type C;
+      DSP_TRY(build_side<T>(p->fs_cols, n1, false));
+      DSP_TRY(build_side<T>(p->fs_rows, kFsCols, false));
+      std::vector<C> hi(static_cast<size_t>(nc / 256)), lo(256);
+      for (int q = 0; q < nc / 256; ++q) {
+        const long double ang = -2.0L * kPiL * static_cast<long double>(q) * 256.0L / static_cast<long double>(nc);
+        hi[static_cast<size_t>(q)].x = static_cast<T>(cosl(ang));
+        hi[static_cast<size_t>(q)].y = static_cast<T>(sinl(ang));
+      }
+      for (int r = 0; r < 256; ++r) {
+        const long double ang = -2.0L * kPiL * static_cast<long double>(r) / static_cast<long double>(nc);
+        lo[static_cast<size_t>(r)].x = static_cast<T>(cosl(ang));
+        lo[static_cast<size_t>(r)].y = static_cast<T>(sinl(ang));
+      }
+      DSP_CUDA(cudaMalloc(&p->d_fs_hi, hi.size() * sizeof(C)));
+      DSP_CUDA(cudaMemcpy(p->d_fs_hi, hi.data(), hi.size() * sizeof(C), cudaMemcpyHostToDevice));
+      DSP_CUDA(cudaMalloc(&p->d_fs_lo, lo.size() * sizeof(C)));
+      DSP_CUDA(cudaMemcpy(p->d_fs_lo, lo.data(), lo.size() * sizeof(C), cudaMemcpyHostToDevice));
+      p->fs_n1 = n1;
+    }
+  }
   if (p->hann) {
     std::vector<T> w(static_cast<size_t>(N));
     for (int k = 0; k < N; ++k) {
@@ -833,6 +1006,24 @@ static int launch_combine(const FftArgs<T>& a, const typename Cpx<T>::type* ws, 
   return after_launch("fft_combine_kernel");
 }
 
+template <typename T, int N1>
+static int launch_four_step(const FftArgs<T>& a, const FourStep<T>& fs, long long cnt, cudaStream_t stream) {
+  typedef typename Cpx<T>::type C;
+  constexpr int NC = N1 * kFsCols;
+  const size_t smem1 = (static_cast<size_t>(kFsTile) * fs_pitch<N1>() + NC / 256 + 256) * sizeof(C);
+  const size_t smem2 = static_cast<size_t>(2 * kFsTile) * fs_pitch<kFsCols>() * sizeof(C);
+  auto k1 = fft4_cols_kernel<T, N1>;
+  auto k2 = fft4_rows_kernel<T, N1>;
+  DSP_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
+  DSP_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+  const long long b1 = cnt * (kFsCols / kFsTile), b2 = cnt * (N1 / 2 / kFsTile + 1);
+  DSP_CHECK(b1 < (1LL << 31) && b2 < (1LL << 31), "too many transforms in one launch");
+  k1<<<static_cast<unsigned>(b1), N1, smem1, stream>>>(a, fs);
+  DSP_TRY(after_launch("fft4_cols_kernel"));
+  k2<<<static_cast<unsigned>(b2), 256, smem2, stream>>>(a, fs);
+  return after_launch("fft4_rows_kernel");
+}
+
 template <typename T>
 int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_valid, int64_t offset, int64_t hop,
                int64_t n_frames, T* mag, int64_t mfs, int64_t mcs, int64_t channels, void* ws, size_t ws_bytes,
@@ -869,10 +1060,34 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
   // run in chunks whose workspace stays L2-resident between the two kernels
   const int64_t chunk = split_chunk(s, sizeof(C));
   a.out = static_cast<C*>(ws);
+  const bool four_step = p->fs_n1 > 0 && getenv("DSPB200_FFT_NO_FOUR_STEP") == nullptr;
+  FourStep<T> fs{};
+  if (four_step) {
+    fs.tw_cols = static_cast<const C*>(p->fs_cols.d_tw_pass);
+    fs.tw_rows = static_cast<const C*>(p->fs_rows.d_tw_pass);
+    for (int i = 0; i < 8; ++i) {
+      fs.tw_cols_offset[i] = p->fs_cols.tw_offset[i];
+      fs.tw_rows_offset[i] = p->fs_rows.tw_offset[i];
+    }
+    fs.tw_hi = static_cast<const C*>(p->d_fs_hi);
+    fs.tw_lo = static_cast<const C*>(p->d_fs_lo);
+    fs.ws = static_cast<C*>(ws);
+  }
   for (int64_t f0 = 0; f0 < n_tr; f0 += chunk) {
     const int64_t cnt = (n_tr - f0) < chunk ? (n_tr - f0) : chunk;
     a.first = f0;
     a.n_items = cnt * s.r_top;
+    if (four_step) {
+      switch (p->fs_n1) {
+        case 128: DSP_TRY((launch_four_step<T, 128>(a, fs, cnt, stream))); break;
+        case 256: DSP_TRY((launch_four_step<T, 256>(a, fs, cnt, stream))); break;
+        case 512: DSP_TRY((launch_four_step<T, 512>(a, fs, cnt, stream))); break;
+        case 1024:
+          if constexpr (sizeof(T) == 4) { DSP_TRY((launch_four_step<T, 1024>(a, fs, cnt, stream))); break; }
+        default: return fail(DSPB200_ERR_UNSUPPORTED, "internal: four-step N1 %d", p->fs_n1);
+      }
+      continue;
+    }
     DSP_TRY((launch_stockham<T, 1>(a, stream)));
     DSP_TRY((launch_combine<T, true>(a, static_cast<const C*>(ws), cnt, stream)));
   }
@@ -987,7 +1202,9 @@ int dspb200_fft_plan_create(int n_fft, int hann, int dtype, dspb200_fft_plan** p
 
 int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
   if (!p) return DSPB200_OK;
-  FftSide* sides[2] = {&p->real_side, &p->c2c_side};
+  cudaFree(p->d_fs_hi);
+  cudaFree(p->d_fs_lo);
+  FftSide* sides[4] = {&p->real_side, &p->c2c_side, &p->fs_cols, &p->fs_rows};
   for (FftSide* s : sides) {
     cudaFree(s->d_tw_pass);
     cudaFree(s->d_tw_top);
