@@ -608,14 +608,22 @@ constexpr int kFsTile = 16;      // columns per CTA (kernel 1), primary rows per
 
 template <typename T> struct FourStep {
   typedef typename Cpx<T>::type C;
-  const C* tw_cols; int tw_cols_offset[8];   // N1-point passes
-  const C* tw_rows; int tw_rows_offset[8];   // 128-point passes
+  const C* tw_cols; int tw_cols_offset[8];                      // N1-point passes
+  const C* tw_rows; int tw_rows_offset[8]; int tw_rows_total;   // 128-point passes
   const C* tw_hi;                            // W_nc^(256 q), q < nc/256
   const C* tw_lo;                            // W_nc^r, r < 256
   C* ws;
 };
 
 template <int M> __host__ __device__ constexpr int fs_pitch() { return (M + (M >> kPadShift)) | 1; }
+// Row slots of kernel 2: a pitch that is a multiple of 16 elements plus a skew 0,8,1,9,...,7,15.
+// Adjacent rows (one half-warp during the passes) sit 8 elements apart modulo 16, so a run of 8
+// consecutive elements per row is conflict-free; the 16 rows a half-warp reads at one column in
+// the real split all start at different offsets modulo 16.
+constexpr int kFsRowPitch = 160;
+__host__ __device__ __forceinline__ constexpr int fs_row_base(int slot) {
+  return slot * kFsRowPitch + ((slot & 1) << 3) + ((slot & 15) >> 1);
+}
 
 template <typename T, int N1>
 __global__ void __launch_bounds__(N1)
@@ -660,12 +668,23 @@ fft4_cols_kernel(const FftArgs<T> a, const FourStep<T> fs) {
   }
   C* sc = s + c * PITCH;
   ct_passes<T, N1, 0, 1>(tmp, sc, fs.tw_cols, fs.tw_cols_offset, tp);
+  // W_nc^(n2 k1), k1 = tp + u Q:  W^(n2 tp) * (W^(n2 Q))^u.  Two table products give the base and
+  // the step; the powers of the step come from a product tree (<= 4 roundings deep) instead of
+  // sixteen scattered table reads per thread, which were the busiest user of the load/store pipe.
+  auto lookup = [&](int q) { return cmul(s_hi[q >> 8], s_lo[q & 255]); };
+  const C wb = lookup(n2 * tp);
+  C pw[16];
+  pw[1] = lookup(n2 * Q);
+  pw[2] = cmul(pw[1], pw[1]); pw[3] = cmul(pw[2], pw[1]); pw[4] = cmul(pw[2], pw[2]);
+  pw[5] = cmul(pw[4], pw[1]); pw[6] = cmul(pw[4], pw[2]); pw[7] = cmul(pw[4], pw[3]);
+  pw[8] = cmul(pw[4], pw[4]);
+#pragma unroll
+  for (int u = 9; u < 16; ++u) pw[u] = cmul(pw[8], pw[u - 8]);
   C* o = fs.ws + fl * NC + n2;
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const int k1 = tp + u * Q;
-    const int q = n2 * k1;
-    const C w = cmul(s_hi[q >> 8], s_lo[q & 255]);
+    const C w = u == 0 ? wb : cmul(wb, pw[u]);
     o[static_cast<long long>(k1) * kFsCols] = cmul(sc[padded(k1)], w);
   }
 }
@@ -674,12 +693,14 @@ template <typename T, int N1>
 __global__ void __launch_bounds__(256)
 fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
   typedef typename Cpx<T>::type C;
-  constexpr int M = kFsCols, Q = M / 16, NC = N1 * M, PITCH = fs_pitch<M>();
+  constexpr int M = kFsCols, Q = M / 16, NC = N1 * M;
   constexpr int G = N1 / 2 / kFsTile;     // groups of 16 primary rows k1 in [1, N1/2]; block G of a frame is row 0
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* s = reinterpret_cast<C*>(smem_raw);
+  C* s_tw = s + 2 * kFsTile * kFsRowPitch;
   const int t = threadIdx.x;
   const int tp = t % Q, slot = t / Q;     // 32 row slots: 0..15 primary rows, 16..31 their mirrors (ascending)
+  for (int i = t; i < fs.tw_rows_total; i += 256) s_tw[i] = fs.tw_rows[i];
   const long long fl = blockIdx.x / (G + 1);
   const int g = static_cast<int>(blockIdx.x - fl * (G + 1));
   const long long f = a.first + fl;
@@ -695,17 +716,28 @@ fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) { tmp[u].x = T(0); tmp[u].y = T(0); }
   }
-  ct_passes<T, M, 0, 1>(tmp, s + slot * PITCH, fs.tw_rows, fs.tw_rows_offset, tp);
+  // the real-split twiddles of this thread's bins, requested before the passes
+  C twp[M / 16];
+  if (g < G) {
+    const int k1 = kFsTile * g + 1 + (t % kFsTile);
+#pragma unroll
+    for (int i = 0; i < M / 16; ++i) {
+      const int idx = k1 + N1 * (t / kFsTile + 16 * i);
+      twp[i] = a.tw_post[idx <= NC / 2 ? idx : NC - idx];
+    }
+  }
+  __syncthreads();               // pass twiddles are in place
+  ct_passes<T, M, 0, 1>(tmp, s + fs_row_base(slot), s_tw, fs.tw_rows_offset, tp);
 
   const long long ch = f / a.n_frames;
   const long long fr = f - ch * a.n_frames;
   T* mg = a.mag + ch * a.mag_channel_stride + fr * a.mag_frame_stride;
-  auto emit = [&](const C A, const C Bz, int idx) {      // A = Z[idx], Bz = Z[nc - idx], idx <= nc/2
+  auto emit = [&](const C A, const C Bz, int idx, const C wpost) {   // A = Z[idx], Bz = Z[nc - idx], idx <= nc/2
     const C Bc = cconj(Bz);
     C xe, xo;
     xe.x = T(0.5) * (A.x + Bc.x); xe.y = T(0.5) * (A.y + Bc.y);
     xo.x = T(0.5) * (A.y - Bc.y); xo.y = T(-0.5) * (A.x - Bc.x);
-    const C tt = cmul(a.tw_post[idx], xo);
+    const C tt = cmul(wpost, xo);
     const C p = cadd(xe, tt), q = csub(xe, tt);
     mg[idx] = finish_mag(p.x * p.x + p.y * p.y, a.db);
     mg[NC - idx] = finish_mag(q.x * q.x + q.y * q.y, a.db);
@@ -713,8 +745,8 @@ fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
   if (g < G) {
     const int j = t % kFsTile;
     const int k1 = kFsTile * g + 1 + j;
-    const C* pa = s + j * PITCH;
-    const C* pb = s + (2 * kFsTile - 1 - j) * PITCH;     // row N1 - k1
+    const C* pa = s + fs_row_base(j);
+    const C* pb = s + fs_row_base(2 * kFsTile - 1 - j);  // row N1 - k1
 #pragma unroll
     for (int i = 0; i < M / 16; ++i) {
       const int k2 = t / kFsTile + 16 * i;
@@ -722,13 +754,13 @@ fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
       const C Bz = pb[padded(M - 1 - k2)];
       const int idx = k1 + N1 * k2;
       if (idx <= NC / 2) {
-        if (2 * k1 != N1 || k2 < M / 2) emit(A, Bz, idx);  // row N1/2 pairs with itself: take each pair once
+        if (2 * k1 != N1 || k2 < M / 2) emit(A, Bz, idx, twp[i]);  // row N1/2 pairs with itself: take each pair once
       } else if (2 * k1 != N1) {
-        emit(Bz, A, NC - idx);
+        emit(Bz, A, NC - idx, twp[i]);
       }
     }
   } else if (t <= M / 2) {                                 // row 0 pairs with itself, k2 <-> (M - k2) mod M
-    emit(s[padded(t)], s[padded((M - t) & (M - 1))], N1 * t);
+    emit(s[padded(t)], s[padded((M - t) & (M - 1))], N1 * t, a.tw_post[N1 * t]);
   }
 }
 
@@ -1011,7 +1043,7 @@ static int launch_four_step(const FftArgs<T>& a, const FourStep<T>& fs, long lon
   typedef typename Cpx<T>::type C;
   constexpr int NC = N1 * kFsCols;
   const size_t smem1 = (static_cast<size_t>(kFsTile) * fs_pitch<N1>() + NC / 256 + 256) * sizeof(C);
-  const size_t smem2 = static_cast<size_t>(2 * kFsTile) * fs_pitch<kFsCols>() * sizeof(C);
+  const size_t smem2 = (static_cast<size_t>(2 * kFsTile) * kFsRowPitch + fs.tw_rows_total) * sizeof(C);
   auto k1 = fft4_cols_kernel<T, N1>;
   auto k2 = fft4_rows_kernel<T, N1>;
   DSP_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
@@ -1069,6 +1101,7 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
       fs.tw_cols_offset[i] = p->fs_cols.tw_offset[i];
       fs.tw_rows_offset[i] = p->fs_rows.tw_offset[i];
     }
+    fs.tw_rows_total = p->fs_rows.tw_total;
     fs.tw_hi = static_cast<const C*>(p->d_fs_hi);
     fs.tw_lo = static_cast<const C*>(p->d_fs_lo);
     fs.ws = static_cast<C*>(ws);
