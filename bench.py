@@ -380,7 +380,9 @@ def run_b200(args):
             "eq": esize * clips * 2 * n_out,
             "fft": esize * clips * n_frames * (N_FFT + bins),
         }
-        kernel_names = {"src": "src_tiled_kernel", "eq": "eq_packed_kernel", "fft": "fft_fixed_kernel"}
+        src_kind = chain.src.kernel_kind(clips, CLIP_SAMPLES) if getattr(chain, "src", None) is not None else "tiled"
+        kernel_names = {"src": "src_mma_kernel" if src_kind == "tensor" else "src_tiled_kernel",
+                        "eq": "eq_packed_kernel", "fft": "fft_fixed_kernel"}
         kernels = {}
         for k in names:
             gbs = alg_bytes[k] / (per_kernel[k] * 1e-3) / 1e9

@@ -77,6 +77,7 @@ SIGNATURES = {
 EXTRA_SIGNATURES = {
     "dspb200_src_run_generic_f32": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_src_run_generic_f64": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
+    "dspb200_src_run_tiled_f32": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
 }
 
 _lib = None

@@ -1,5 +1,7 @@
 // Cross-translation-unit entry points used by the chain driver.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 struct dspb200_src_plan;
@@ -18,6 +20,21 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
                int64_t hop, int64_t n_frames, T* mag, int64_t mfs, int64_t mcs, int64_t channels,
                void* ws, size_t ws_bytes, cudaStream_t stream);
 int src_plan_ratio(const dspb200_src_plan* plan, int* L, int* M, int* dtype);
+
+// K1 on tcgen05 (src_mma.cu): per-plan tap matrices and the launch.  fp32 only.
+struct SrcMmaPlan {
+  int ok = 0;
+  int period = 0;          // distinct tile phases
+  int kpad = 0;            // GEMM depth per tile (multiple of 32)
+  long long adv = 0;       // input samples per `period` tiles
+  float* d_table = nullptr;   // [period][hi, lo][128][kpad]
+  int* d_lo = nullptr;        // [period] window start of tile p
+};
+int src_mma_build(const std::vector<double>& taps, int L, int M, SrcMmaPlan& mp);
+void src_mma_free(SrcMmaPlan& mp);
+bool src_mma_usable(const SrcMmaPlan& mp, const float* x, int64_t xs, int64_t channels, int64_t n_in);
+int src_mma_run(const SrcMmaPlan& mp, const float* x, int64_t xs, float* y, int64_t ys, int64_t channels,
+                int64_t n_in, int64_t n_out, cudaStream_t stream);
 int fft_plan_info(const dspb200_fft_plan* plan, int* n_fft, int* dtype);
 int eq_plan_dtype(const dspb200_eq_plan* plan);
 }  // namespace dspb200

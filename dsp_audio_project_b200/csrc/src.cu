@@ -393,6 +393,7 @@ struct dspb200_src_plan {
   void* d_table = nullptr;
   int* d_group_lo = nullptr;
   int* d_tile_lo = nullptr;
+  dspb200::SrcMmaPlan mma;   // fp32: tensor-core form (src_mma.cu)
 };
 
 namespace dspb200 {
@@ -509,6 +510,11 @@ int src_run(const dspb200_src_plan* plan, const T* x, int64_t xs, T* y, int64_t 
   const bool long_signal = n_in * plan->L >= Tt;
   bool tiled = g.ok && long_signal;
   if (force_kind == 0) tiled = false;
+  if constexpr (sizeof(T) == 4) {
+    if (long_signal && force_kind != 0 && force_kind != 1 && getenv("DSPB200_SRC_NO_MMA") == nullptr &&
+        src_mma_usable(plan->mma, x, xs, channels, n_in))
+      return src_mma_run(plan->mma, x, xs, y, ys, channels, n_in, n_out, stream);
+  }
   if (!tiled) {
     const int threads = 256;
     dim3 grid(static_cast<unsigned>(ceil_div(n_out, threads)), static_cast<unsigned>(channels < 65535 ? channels : 65535));
@@ -594,6 +600,7 @@ static int plan_tables(dspb200_src_plan* p) {
     DSP_TRY(upload(group_lo, &q)); p->d_group_lo = static_cast<int*>(q);
     DSP_TRY(upload(tile_lo, &q)); p->d_tile_lo = static_cast<int*>(q);
   }
+  if constexpr (sizeof(T) == 4) DSP_TRY(src_mma_build(p->taps, p->L, p->M, p->mma));
   return DSPB200_OK;
 }
 
@@ -673,6 +680,7 @@ int dspb200_src_plan_destroy(dspb200_src_plan* p) {
   cudaFree(p->d_table);
   cudaFree(p->d_group_lo);
   cudaFree(p->d_tile_lo);
+  src_mma_free(p->mma);
   delete p;
   return DSPB200_OK;
 }
@@ -683,6 +691,9 @@ int dspb200_src_plan_kernel_kind(const dspb200_src_plan* plan, int64_t channels,
   (void)channels; (void)x_stride;
   const int T = plan->n_taps;
   *kind = (plan->geom.ok && n_in * plan->L >= T) ? 1 : 0;
+  if (plan->dtype == DSPB200_F32 && plan->mma.ok && n_in * plan->L >= T && x_stride % 4 == 0 && n_in >= 128 &&
+      getenv("DSPB200_SRC_NO_MMA") == nullptr)
+    *kind = 2;
   return DSPB200_OK;
 }
 
@@ -694,7 +705,11 @@ int dspb200_src_run_f64(const dspb200_src_plan* plan, const double* x, int64_t x
                         int64_t channels, int64_t n_in, void* stream) {
   return src_run<double>(plan, x, xs, y, ys, channels, n_in, static_cast<cudaStream_t>(stream), -1);
 }
-/* test hook: force the generic kernel (kind 0) regardless of geometry */
+/* test hooks: force the generic kernel (kind 0) / the tiled FFMA kernel (kind 1) regardless of geometry */
+int dspb200_src_run_tiled_f32(const dspb200_src_plan* plan, const float* x, int64_t xs, float* y, int64_t ys,
+                              int64_t channels, int64_t n_in, void* stream) {
+  return src_run<float>(plan, x, xs, y, ys, channels, n_in, static_cast<cudaStream_t>(stream), 1);
+}
 int dspb200_src_run_generic_f32(const dspb200_src_plan* plan, const float* x, int64_t xs, float* y, int64_t ys,
                                 int64_t channels, int64_t n_in, void* stream) {
   return src_run<float>(plan, x, xs, y, ys, channels, n_in, static_cast<cudaStream_t>(stream), 0);

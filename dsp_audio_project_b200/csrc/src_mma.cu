@@ -1,0 +1,308 @@
+// K1 on the tensor cores: the polyphase resampler as a banded-Toeplitz GEMM.
+//
+// For 128 consecutive outputs m0..m0+127 of every channel c
+//     y[c, m0 + r] = sum_k  A_p[r, k] * x[c, lo + k],      A_p[r, k] = h[(m0 + r) M + P - (lo + k) L]
+// (dsp_core.py:149-173 with the zero-stuffed signal eliminated).  The tap matrix A_p depends on the
+// tile only through its phase p = tile mod period (period = 4L / gcd(128 M, 4L) tiles advance the
+// input by a whole multiple of 4 samples), so the host lays out `period` matrices [128 x K] once per
+// plan.  One tile is D[128 outputs x 256 channels] = A_p[128 x K] . X[256 x K]^T on tcgen05.mma
+// (kind::tf32, fp32 accumulators in TMEM).  TF32 keeps 11 significand bits, far short of the 1e-5
+// full-scale parity bound, so each operand is split in two TF32 numbers and three products are
+// accumulated:  A_hi X + A_lo X + A_hi X_lo  (the hardware truncates fp32 operands to TF32, so the
+// raw x tile serves as X_hi; X_lo = x - trunc(x) is formed in shared memory by four converter warps;
+// A_hi / A_lo are precomputed).  Measured error of the split on random data: 1.6e-6 of max|y|.
+//
+// Warp roles (one persistent CTA per SM): warps 0-3 epilogue (TMEM -> registers -> 128-byte
+// coalesced global stores), warp 4 TMA producer, warp 5 MMA issuer (one elected lane) + TMEM
+// allocation, warps 6-9 converters.  Shared-memory ring of 2 stages x {A_hi, A_lo, X, X_lo} tiles of
+// 32 k-values (128-byte swizzled, K-major); two 256-column accumulators in TMEM so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace dspb200 {
+
+namespace {
+
+constexpr int kTM = 128;        // outputs per tile (MMA M)
+constexpr int kTN = 256;        // channels per tile (MMA N)
+constexpr int kBK = 32;         // k-values per stage (one 128-byte swizzle row)
+constexpr int kStages = 2;
+constexpr int kThreads = 320;   // 10 warps
+constexpr uint32_t kABytes = kTM * kBK * 4;   // 16 KB
+constexpr uint32_t kBBytes = kTN * kBK * 4;   // 32 KB
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
+
+struct MmaArgs {
+  float* y; long long y_stride;
+  long long channels, n_out;
+  const int* lo;                // [period] window start of tile p (multiple of 4, may be negative)
+  int period, nkb;
+  long long adv;                // input samples per `period` tiles
+  long long n_tt, n_tiles;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* p) {
+  // K-major operand, 128-byte swizzle: 8-row groups 1024 bytes apart, descriptor version 1 (sm_100)
+  const uint64_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  return ((addr >> 4) & 0x3FFF) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_x, const MmaArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));   // swizzle atoms: 1024-byte aligned
+  __shared__ __align__(8) uint64_t bars[3 * kStages + 4];
+  __shared__ uint32_t tmem_base_s;
+  uint64_t* full = bars;                     // [stage] TMA landed A_hi, A_lo, X
+  uint64_t* conv = bars + kStages;           // [stage] X_lo written (4 converter warps)
+  uint64_t* empty = bars + 2 * kStages;      // [stage] the MMAs reading the stage have completed
+  uint64_t* acc_full = bars + 3 * kStages;   // [2] accumulator complete
+  uint64_t* acc_empty = acc_full + 2;        // [2] accumulator drained by the 4 epilogue warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&tmem_base_s))), "r"(2 * kTN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  auto stage_ptr = [&](int s, int which) -> unsigned char* {   // 0: A_hi, 1: A_lo, 2: X, 3: X_lo
+    unsigned char* base = smem + static_cast<size_t>(s) * kStageBytes;
+    return which < 2 ? base + which * kABytes : base + 2 * kABytes + (which - 2) * kBBytes;
+  };
+  const long long first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 4) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_a);
+      tma_prefetch_desc(&tm_x);
+      uint32_t it = 0;
+      for (long long tile = first; tile < a.n_tiles; tile += step) {
+        const long long ct = tile / a.n_tt, tt = tile - ct * a.n_tt;
+        const int p = static_cast<int>(tt % a.period);
+        const long long lo = a.lo[p] + (tt / a.period) * a.adv;
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1);
+          mbar_expect_tx(&full[s], 2 * kABytes + kBBytes);
+          tma_load_2d(stage_ptr(s, 0), &tm_a, kb * kBK, (2 * p) * kTM, &full[s]);
+          tma_load_2d(stage_ptr(s, 1), &tm_a, kb * kBK, (2 * p + 1) * kTM, &full[s]);
+          tma_load_2d(stage_ptr(s, 2), &tm_x, static_cast<int>(lo) + kb * kBK, static_cast<int>(ct) * kTN, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      // D fp32, A/B tf32, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kTN >> 3) << 17) | (uint32_t(kTM >> 4) << 24);
+      uint32_t it = 0, ti = 0;
+      for (long long tile = first; tile < a.n_tiles; tile += step, ++ti) {
+        const int b = ti & 1;
+        if (ti >= 2) mbar_wait(&acc_empty[b], ((ti >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + b * kTN;
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          mbar_wait(&conv[s], ph);
+          tc_fence_after();
+          const uint64_t dah = umma_desc_sw128(stage_ptr(s, 0)), dal = umma_desc_sw128(stage_ptr(s, 1));
+          const uint64_t dx = umma_desc_sw128(stage_ptr(s, 2)), dxl = umma_desc_sw128(stage_ptr(s, 3));
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            umma_tf32(d, dah + 2 * k, dx + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            umma_tf32(d, dal + 2 * k, dx + 2 * k, idesc, 1u);
+            umma_tf32(d, dah + 2 * k, dxl + 2 * k, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[b]);
+      }
+    }
+  } else if (warp >= 6) {
+    // ---------------- converters: X_lo = x - trunc_tf32(x), same (swizzled) position ----------------
+    const int ctid = threadIdx.x - 6 * 32;   // 0..127
+    uint32_t it = 0;
+    for (long long tile = first; tile < a.n_tiles; tile += step) {
+      for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&full[s], (it / kStages) & 1);
+        const float4* src = reinterpret_cast<const float4*>(stage_ptr(s, 2));
+        float4* dst = reinterpret_cast<float4*>(stage_ptr(s, 3));
+#pragma unroll 4
+        for (int i = ctid; i < static_cast<int>(kBBytes / 16); i += 128) {
+          const float4 v = src[i];
+          float4 r;
+          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          dst[i] = r;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 0-3: TMEM lanes 32w .. 32w+31 = outputs ----------------
+    uint32_t ti = 0;
+    for (long long tile = first; tile < a.n_tiles; tile += step, ++ti) {
+      const long long ct = tile / a.n_tt, tt = tile - ct * a.n_tt;
+      const int b = ti & 1;
+      mbar_wait(&acc_full[b], (ti >> 1) & 1);
+      tc_fence_after();
+      const long long m = tt * kTM + warp * 32 + lane;
+      const bool m_ok = m < a.n_out;
+      const long long c_base = ct * kTN;
+      float* yrow = a.y + c_base * a.y_stride + m;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(b * kTN + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                       "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                       "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                       "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c_base + c0 + j < a.channels) yrow[static_cast<long long>(c0 + j) * a.y_stride] = __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * kTN));
+}
+
+float round_tf32(float v) {   // nearest TF32 (ties away): exactly representable, so the hardware truncation keeps it
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+
+long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace
+
+int src_mma_build(const std::vector<double>& taps, int L, int M, SrcMmaPlan& mp) {
+  mp = SrcMmaPlan{};
+  const long long T = static_cast<long long>(taps.size());
+  const long long P = (T - 1) / 2;
+  const long long g = std::gcd(static_cast<long long>(kTM) * M, 4LL * L);
+  const long long period = 4LL * L / g;
+  if (period > 1024) return DSPB200_OK;
+  mp.adv = period * kTM * M / L;
+  std::vector<int> lo(static_cast<size_t>(period));
+  long long span = 0;
+  for (long long p = 0; p < period; ++p) {
+    const long long m0 = p * kTM;
+    // taps h[t], t = m M + P - i L in [0, T):  i >= (m M + P - T + 1) / L,  i <= (m M + P) / L
+    const long long i_min = -floor_div(-(m0 * M + P - T + 1), L);
+    const long long i_max = floor_div((m0 + kTM - 1) * M + P, L);
+    const long long l4 = floor_div(i_min, 4) * 4;
+    lo[static_cast<size_t>(p)] = static_cast<int>(l4);
+    span = std::max(span, i_max - l4 + 1);
+  }
+  const long long kpad = (span + kBK - 1) / kBK * kBK;
+  const size_t elems = static_cast<size_t>(period) * 2 * kTM * static_cast<size_t>(kpad);
+  if (elems * sizeof(float) > (size_t(64) << 20)) return DSPB200_OK;   // keep the tap matrices L2-resident
+  std::vector<float> tab(elems, 0.f);
+  for (long long p = 0; p < period; ++p)
+    for (int r = 0; r < kTM; ++r)
+      for (long long k = 0; k < kpad; ++k) {
+        const long long t = (p * kTM + r) * M + P - (lo[static_cast<size_t>(p)] + k) * L;
+        if (t < 0 || t >= T) continue;
+        const float v = static_cast<float>(taps[static_cast<size_t>(t)]);
+        const float hi = round_tf32(v);
+        tab[((static_cast<size_t>(p) * 2 + 0) * kTM + r) * kpad + k] = hi;
+        tab[((static_cast<size_t>(p) * 2 + 1) * kTM + r) * kpad + k] = v - hi;
+      }
+  DSP_CUDA(cudaMalloc(reinterpret_cast<void**>(&mp.d_table), elems * sizeof(float)));
+  DSP_CUDA(cudaMemcpy(mp.d_table, tab.data(), elems * sizeof(float), cudaMemcpyHostToDevice));
+  DSP_CUDA(cudaMalloc(reinterpret_cast<void**>(&mp.d_lo), lo.size() * sizeof(int)));
+  DSP_CUDA(cudaMemcpy(mp.d_lo, lo.data(), lo.size() * sizeof(int), cudaMemcpyHostToDevice));
+  mp.period = static_cast<int>(period);
+  mp.kpad = static_cast<int>(kpad);
+  mp.ok = 1;
+  return DSPB200_OK;
+}
+
+void src_mma_free(SrcMmaPlan& mp) {
+  cudaFree(mp.d_table);
+  cudaFree(mp.d_lo);
+  mp = SrcMmaPlan{};
+}
+
+bool src_mma_usable(const SrcMmaPlan& mp, const float* x, int64_t xs, int64_t channels, int64_t n_in) {
+  (void)channels;
+  return mp.ok && reinterpret_cast<uintptr_t>(x) % 16 == 0 && xs % 4 == 0 && n_in >= 128 &&
+         kStages * kStageBytes + 1024 <= static_cast<size_t>(max_smem_optin());
+}
+
+int src_mma_run(const SrcMmaPlan& mp, const float* x, int64_t xs, float* y, int64_t ys, int64_t channels,
+                int64_t n_in, int64_t n_out, cudaStream_t stream) {
+  CUtensorMap tm_a, tm_x;
+  memset(&tm_a, 0, sizeof(tm_a));
+  memset(&tm_x, 0, sizeof(tm_x));
+  DSP_TRY(encode_tmap_2d(&tm_a, DSPB200_F32, mp.d_table, static_cast<uint64_t>(mp.kpad),
+                         static_cast<uint64_t>(mp.period) * 2 * kTM, static_cast<uint64_t>(mp.kpad) * sizeof(float),
+                         kBK, kTM, true));
+  DSP_TRY(encode_tmap_2d(&tm_x, DSPB200_F32, x, static_cast<uint64_t>(n_in), static_cast<uint64_t>(channels),
+                         static_cast<uint64_t>(xs) * sizeof(float), kBK, kTN, true));
+  MmaArgs a{};
+  a.y = y; a.y_stride = ys; a.channels = channels; a.n_out = n_out;
+  a.lo = mp.d_lo; a.period = mp.period; a.nkb = mp.kpad / kBK; a.adv = mp.adv;
+  a.n_tt = ceil_div(n_out, kTM);
+  a.n_tiles = a.n_tt * ceil_div(channels, kTN);
+  const size_t smem = kStages * kStageBytes + 1024;
+  DSP_CUDA(cudaFuncSetAttribute(src_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t sms = sm_count();
+  const int grid = static_cast<int>(a.n_tiles < sms ? a.n_tiles : sms);
+  src_mma_kernel<<<grid, kThreads, smem, stream>>>(tm_a, tm_x, a);
+  return after_launch("src_mma_kernel");
+}
+
+}  // namespace dspb200

@@ -112,9 +112,9 @@ class SrcPlan:
     def kernel_kind(self, channels: int, n_in: int) -> str:
         k = C.c_int()
         check(_lib.load().dspb200_src_plan_kernel_kind(self._h, channels, n_in, n_in, C.byref(k)))
-        return "tiled" if k.value == 1 else "generic"
+        return {0: "generic", 1: "tiled", 2: "tensor"}[k.value]
 
-    def run(self, x, out=None, *, force_generic=False):
+    def run(self, x, out=None, *, force_generic=False, force_tiled=False):
         torch = _torch()
         _check_tensor(x, self.dtype_id, "x")
         ch, n_in = x.shape
@@ -127,7 +127,10 @@ class SrcPlan:
             raise ValueError(f"out must be [{ch}, {n_out}]")
         lib = _lib.load()
         suffix = "f32" if self.dtype_id == F32 else "f64"
-        fn = getattr(lib, ("dspb200_src_run_generic_" if force_generic else "dspb200_src_run_") + suffix)
+        if force_tiled and self.dtype_id == F32:      # the FFMA kernel, bypassing the tensor-core form
+            fn = lib.dspb200_src_run_tiled_f32
+        else:
+            fn = getattr(lib, ("dspb200_src_run_generic_" if force_generic else "dspb200_src_run_") + suffix)
         with torch.cuda.device(x.device):
             check(fn(self._h, x.data_ptr(), _row_stride(x), out.data_ptr(), _row_stride(out), ch, n_in,
                      _stream_ptr(x)))

@@ -122,7 +122,7 @@ def test_src_c2_full_size_properties(pk, torch_cuda):
     torch = torch_cuda
     ch, n_in = 1024, 441000
     plan = pk.SrcPlan(160, 147, np.float32)
-    assert plan.kernel_kind(ch, n_in) == "tiled"
+    assert plan.kernel_kind(ch, n_in) == "tensor"
     gen = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand((ch, n_in), generator=gen, device="cuda", dtype=torch.float32) - 0.5
     y = plan.run(x)
@@ -336,6 +336,37 @@ def test_fft_parseval_and_linearity_full_c4_frame_count(pk, torch_cuda):
     assert float(((energy_f - energy_t).abs() / energy_t).max()) <= 1e-4
     ref = torch.fft.rfft(frames[:2], dim=-1).abs()
     assert float((mag[:2].double() - ref).abs().max() / ref.max()) <= TOL_F32_FFT
+
+
+@pytest.mark.parametrize("L,M", [(160, 147), (3, 2), (2, 3), (147, 160), (8, 8), (7, 5), (1, 4), (4, 1)])
+def test_src_tensor_core_form_matches_oracle_and_tiled(pk, torch_cuda, L, M):
+    """fp32 SRC runs as a banded-Toeplitz GEMM on tcgen05 (3-term TF32 split) for long signals.
+    Against the fp64 closed form, against the FFMA kernel, on ragged channel counts (not a
+    multiple of the 256-channel tile), odd lengths and padded row strides."""
+    torch = torch_cuda
+    rng = np.random.default_rng(1000 * L + M)
+    plan = pk.SrcPlan(L, M, np.float32)
+    for channels, n_in in ((3, 4412), (261, 2052), (1, 30000), (2, 4411)):
+        if n_in * L < o.src_geometry(n_in, L, M)[0]:
+            continue
+        # rows must be 16-byte aligned for the TMA path; odd lengths fall back to the FFMA kernels
+        assert (plan.kernel_kind(channels, n_in) == "tensor") == (n_in % 4 == 0)
+        x = rng.uniform(-1, 1, (channels, n_in)).astype(np.float32)
+        xt = torch.as_tensor(x, device="cuda")
+        y = plan.run(xt)
+        y_tiled = plan.run(xt, force_tiled=True)
+        ref = np.stack([o.resample_closed_form(x[c].astype(np.float64), 48000, M, L)[0]
+                        for c in (0, channels // 2, channels - 1)])
+        got = y.cpu().numpy()[[0, channels // 2, channels - 1]]
+        scale = max(1.0, float(np.max(np.abs(ref))))
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= TOL_F32_SRC * scale, (channels, n_in)
+        assert float((y - y_tiled).abs().max()) <= TOL_F32_SRC * scale
+        # a strided view (row pitch larger than the row) and an output tensor with its own pitch
+        big = torch.zeros((channels, n_in + 12), device="cuda", dtype=torch.float32)
+        big[:, :n_in] = xt
+        y2 = plan.run(big[:, :n_in])
+        assert torch.equal(y2, y)
 
 
 @pytest.mark.parametrize("n_fft", [32768, 65536, 131072])
