@@ -691,8 +691,8 @@ int dspb200_src_plan_kernel_kind(const dspb200_src_plan* plan, int64_t channels,
   (void)channels; (void)x_stride;
   const int T = plan->n_taps;
   *kind = (plan->geom.ok && n_in * plan->L >= T) ? 1 : 0;
-  if (plan->dtype == DSPB200_F32 && plan->mma.ok && n_in * plan->L >= T && x_stride % 4 == 0 && n_in >= 128 &&
-      getenv("DSPB200_SRC_NO_MMA") == nullptr)
+  if (plan->dtype == DSPB200_F32 && n_in * plan->L >= T && getenv("DSPB200_SRC_NO_MMA") == nullptr &&
+      src_mma_usable(plan->mma, nullptr, x_stride, channels, n_in))
     *kind = 2;
   return DSPB200_OK;
 }

@@ -9,14 +9,15 @@
 // (kind::tf32, fp32 accumulators in TMEM).  TF32 keeps 11 significand bits, far short of the 1e-5
 // full-scale parity bound, so each operand is split in two TF32 numbers and three products are
 // accumulated:  A_hi X + A_lo X + A_hi X_lo  (the hardware truncates fp32 operands to TF32, so the
-// raw x tile serves as X_hi; X_lo = x - trunc(x) is formed in shared memory by four converter warps;
+// raw x tile serves as X_hi; X_lo = x - trunc(x) is formed in shared memory by the converter warps;
 // A_hi / A_lo are precomputed).  Measured error of the split on random data: 1.6e-6 of max|y|.
 //
-// Warp roles (one persistent CTA per SM): warps 0-3 epilogue (TMEM -> registers -> 128-byte
-// coalesced global stores), warp 4 TMA producer, warp 5 MMA issuer (one elected lane) + TMEM
-// allocation, warps 6-9 converters.  Shared-memory ring of 2 stages x {A_hi, A_lo, X, X_lo} tiles of
+// Warp roles (one persistent CTA per SM): warps 0-7 epilogue (TMEM -> registers -> 128-byte
+// coalesced global stores), warp 8 TMA producer, warp 9 MMA issuer (one elected lane) + TMEM
+// allocation, warps 10-13 converters.  Shared-memory ring of 2 stages x {A_hi, A_lo, X, X_lo} tiles of
 // 32 k-values (128-byte swizzled, K-major); two 256-column accumulators in TMEM so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -32,7 +33,10 @@ constexpr int kTM = 128;        // outputs per tile (MMA M)
 constexpr int kTN = 256;        // channels per tile (MMA N)
 constexpr int kBK = 32;         // k-values per stage (one 128-byte swizzle row)
 constexpr int kStages = 2;
-constexpr int kThreads = 320;   // 10 warps
+constexpr int kEpiWarps = 8;    // two per TMEM lane quarter: columns [0,128) and [128,256)
+constexpr int kConvWarps = 4;
+constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kConvWarp0 = kEpiWarps + 2;
+constexpr int kThreads = (kConvWarp0 + kConvWarps) * 32;
 constexpr uint32_t kABytes = kTM * kBK * 4;   // 16 KB
 constexpr uint32_t kBBytes = kTN * kBK * 4;   // 32 KB
 constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
@@ -44,6 +48,7 @@ struct MmaArgs {
   int period, nkb;
   long long adv;                // input samples per `period` tiles
   long long n_tt, n_tiles;
+  int dbg;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(const void* p) {
@@ -59,6 +64,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t* v, uint32_t taddr) {   // 32 lanes x 32 columns, one column per register
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr));
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -78,11 +93,11 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], kConvWarps); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&tmem_base_s))), "r"(2 * kTN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -98,7 +113,7 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   };
   const long long first = blockIdx.x, step = gridDim.x;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       tma_prefetch_desc(&tm_a);
@@ -111,14 +126,17 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
           const int s = it % kStages;
           if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1);
-          mbar_expect_tx(&full[s], 2 * kABytes + kBBytes);
-          tma_load_2d(stage_ptr(s, 0), &tm_a, kb * kBK, (2 * p) * kTM, &full[s]);
-          tma_load_2d(stage_ptr(s, 1), &tm_a, kb * kBK, (2 * p + 1) * kTM, &full[s]);
-          tma_load_2d(stage_ptr(s, 2), &tm_x, static_cast<int>(lo) + kb * kBK, static_cast<int>(ct) * kTN, &full[s]);
+          mbar_expect_tx(&full[s], ((a.dbg & 2) ? 0 : 2 * kABytes) + kBBytes);
+          if (!(a.dbg & 2)) {
+            tma_load_2d(stage_ptr(s, 0), &tm_a, kb * kBK, (2 * p) * kTM, &full[s]);
+            tma_load_2d(stage_ptr(s, 1), &tm_a, kb * kBK, (2 * p + 1) * kTM, &full[s]);
+          }
+          if (a.dbg & 1) tma_load_2d(stage_ptr(s, 2), &tm_x, kb * kBK, 0, &full[s]);
+          else tma_load_2d(stage_ptr(s, 2), &tm_x, static_cast<int>(lo) + kb * kBK, static_cast<int>(ct) * kTN, &full[s]);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       // D fp32, A/B tf32, both K-major, N = 256, M = 128
@@ -133,24 +151,29 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full[s], ph);
-          mbar_wait(&conv[s], ph);
           tc_fence_after();
           const uint64_t dah = umma_desc_sw128(stage_ptr(s, 0)), dal = umma_desc_sw128(stage_ptr(s, 1));
           const uint64_t dx = umma_desc_sw128(stage_ptr(s, 2)), dxl = umma_desc_sw128(stage_ptr(s, 3));
+          // the two products with the raw x tile start as soon as TMA has landed; only the third
+          // needs the converters' X_lo, which keeps them off the critical path
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             umma_tf32(d, dah + 2 * k, dx + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            umma_tf32(d, dal + 2 * k, dx + 2 * k, idesc, 1u);
-            umma_tf32(d, dah + 2 * k, dxl + 2 * k, idesc, 1u);
+            if (!(a.dbg & 4)) umma_tf32(d, dal + 2 * k, dx + 2 * k, idesc, 1u);
           }
+          mbar_wait(&conv[s], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k)
+            if (!(a.dbg & 4)) umma_tf32(d, dah + 2 * k, dxl + 2 * k, idesc, 1u);
           umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[b]);
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= kConvWarp0) {
     // ---------------- converters: X_lo = x - trunc_tf32(x), same (swizzled) position ----------------
-    const int ctid = threadIdx.x - 6 * 32;   // 0..127
+    const int ctid = threadIdx.x - kConvWarp0 * 32;   // 0 .. 32*kConvWarps-1
     uint32_t it = 0;
     for (long long tile = first; tile < a.n_tiles; tile += step) {
       for (int kb = 0; kb < a.nkb; ++kb, ++it) {
@@ -159,7 +182,7 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const float4* src = reinterpret_cast<const float4*>(stage_ptr(s, 2));
         float4* dst = reinterpret_cast<float4*>(stage_ptr(s, 3));
 #pragma unroll 4
-        for (int i = ctid; i < static_cast<int>(kBBytes / 16); i += 128) {
+        for (int i = ctid; i < static_cast<int>(kBBytes / 16); i += 32 * kConvWarps) {
           const float4 v = src[i];
           float4 r;
           r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -174,35 +197,40 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
     }
   } else {
-    // ---------------- epilogue warps 0-3: TMEM lanes 32w .. 32w+31 = outputs ----------------
+    // ---------------- epilogue warps 0-7 ----------------
+    // warp w reads TMEM lanes 32(w%4) .. +31 (= outputs) and the column half w/4 (= 128 channels);
+    // every store instruction writes 32 consecutive outputs of one channel (128 bytes)
+    const int quarter = warp & 3, half = warp >> 2;
     uint32_t ti = 0;
     for (long long tile = first; tile < a.n_tiles; tile += step, ++ti) {
       const long long ct = tile / a.n_tt, tt = tile - ct * a.n_tt;
       const int b = ti & 1;
       mbar_wait(&acc_full[b], (ti >> 1) & 1);
       tc_fence_after();
-      const long long m = tt * kTM + warp * 32 + lane;
-      const bool m_ok = m < a.n_out;
-      const long long c_base = ct * kTN;
-      float* yrow = a.y + c_base * a.y_stride + m;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kTN; c0 += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(b * kTN + c0);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                       "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                       "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                       "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m_ok) {
+      const long long m = tt * kTM + quarter * 32 + lane;
+      const bool m_ok = (m < a.n_out) && !(a.dbg & 8);
+      const long long c_first = ct * kTN + half * (kTN / 2);
+      const bool all_channels = c_first + kTN / 2 <= a.channels;
+      float* p = a.y + c_first * a.y_stride + m;
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(b * kTN + half * (kTN / 2));
+      uint32_t v[2][32];
+      tmem_ld32(v[0], taddr);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c_base + c0 + j < a.channels) yrow[static_cast<long long>(c0 + j) * a.y_stride] = __uint_as_float(v[j]);
+      for (int q = 0; q < kTN / 2 / 32; ++q) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (q + 1 < kTN / 2 / 32) tmem_ld32(v[(q + 1) & 1], taddr + (q + 1) * 32);   // in flight during the stores
+        const uint32_t* vv = v[q & 1];
+        if (m_ok) {
+          if (all_channels) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { *p = __uint_as_float(vv[j]); p += a.y_stride; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c_first + q * 32 + j < a.channels) *p = __uint_as_float(vv[j]);
+              p += a.y_stride;
+            }
+          }
         }
       }
       tc_fence_before();
@@ -212,7 +240,7 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * kTN));
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * kTN));
 }
 
 float round_tf32(float v) {   // nearest TF32 (ties away): exactly representable, so the hardware truncation keeps it
@@ -277,7 +305,9 @@ void src_mma_free(SrcMmaPlan& mp) {
 }
 
 bool src_mma_usable(const SrcMmaPlan& mp, const float* x, int64_t xs, int64_t channels, int64_t n_in) {
-  (void)channels;
+  // a tile always multiplies 256 channels: below 3/4 occupancy of the last tile row the FFMA kernel wins
+  const int64_t padded = ceil_div(channels, kTN) * kTN;
+  if (4 * channels < 3 * padded && getenv("DSPB200_SRC_FORCE_MMA") == nullptr) return false;
   return mp.ok && reinterpret_cast<uintptr_t>(x) % 16 == 0 && xs % 4 == 0 && n_in >= 128 &&
          kStages * kStageBytes + 1024 <= static_cast<size_t>(max_smem_optin());
 }
@@ -297,6 +327,7 @@ int src_mma_run(const SrcMmaPlan& mp, const float* x, int64_t xs, float* y, int6
   a.lo = mp.d_lo; a.period = mp.period; a.nkb = mp.kpad / kBK; a.adv = mp.adv;
   a.n_tt = ceil_div(n_out, kTM);
   a.n_tiles = a.n_tt * ceil_div(channels, kTN);
+  a.dbg = getenv("DSPB200_SRC_MMA_DBG") ? atoi(getenv("DSPB200_SRC_MMA_DBG")) : 0;
   const size_t smem = kStages * kStageBytes + 1024;
   DSP_CUDA(cudaFuncSetAttribute(src_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t sms = sm_count();

@@ -339,7 +339,7 @@ def test_fft_parseval_and_linearity_full_c4_frame_count(pk, torch_cuda):
 
 
 @pytest.mark.parametrize("L,M", [(160, 147), (3, 2), (2, 3), (147, 160), (8, 8), (7, 5), (1, 4), (4, 1)])
-def test_src_tensor_core_form_matches_oracle_and_tiled(pk, torch_cuda, L, M):
+def test_src_tensor_core_form_matches_oracle_and_tiled(pk, torch_cuda, L, M, monkeypatch):
     """fp32 SRC runs as a banded-Toeplitz GEMM on tcgen05 (3-term TF32 split) for long signals.
     Against the fp64 closed form, against the FFMA kernel, on ragged channel counts (not a
     multiple of the 256-channel tile), odd lengths and padded row strides."""
@@ -350,6 +350,7 @@ def test_src_tensor_core_form_matches_oracle_and_tiled(pk, torch_cuda, L, M):
         if n_in * L < o.src_geometry(n_in, L, M)[0]:
             continue
         # rows must be 16-byte aligned for the TMA path; odd lengths fall back to the FFMA kernels
+        monkeypatch.setenv("DSPB200_SRC_FORCE_MMA", "1")     # small channel counts normally stay on the FFMA kernel
         assert (plan.kernel_kind(channels, n_in) == "tensor") == (n_in % 4 == 0)
         x = rng.uniform(-1, 1, (channels, n_in)).astype(np.float32)
         xt = torch.as_tensor(x, device="cuda")
@@ -367,6 +368,8 @@ def test_src_tensor_core_form_matches_oracle_and_tiled(pk, torch_cuda, L, M):
         big[:, :n_in] = xt
         y2 = plan.run(big[:, :n_in])
         assert torch.equal(y2, y)
+        monkeypatch.delenv("DSPB200_SRC_FORCE_MMA")
+        assert plan.kernel_kind(channels, n_in) != "tensor" or 4 * channels >= 3 * (-(-channels // 256) * 256)
 
 
 @pytest.mark.parametrize("n_fft", [32768, 65536, 131072])
