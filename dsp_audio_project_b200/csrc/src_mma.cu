@@ -13,10 +13,13 @@
 // A_hi / A_lo are precomputed).  Measured error of the split on random data: 1.6e-6 of max|y|.
 //
 // Warp roles (one persistent CTA per SM): warps 0-7 epilogue (TMEM -> registers -> 128-byte
-// coalesced global stores), warp 8 TMA producer, warp 9 MMA issuer (one elected lane) + TMEM
-// allocation, warps 10-13 converters.  Shared-memory ring of 2 stages x {A_hi, A_lo, X, X_lo} tiles of
-// 32 k-values (128-byte swizzled, K-major); two 256-column accumulators in TMEM so the epilogue of
-// tile i overlaps the MMAs of tile i+1.
+// coalesced global stores), warp 8 TMA producer of x tiles, warp 9 MMA issuer (one elected lane) +
+// TMEM allocation, warp 10 TMA producer of tap tiles, warps 11-14 converters.  Tiles hold 32 k-values
+// (128-byte swizzled, K-major).  The x ring is 4 deep (HBM latency), the A_hi ring 4 and the A_lo ring 2 deep (L2 hits).
+// Per k-block the issuer runs the two products that read the raw x tile, the converters then
+// overwrite the tile in place with X_lo, and the third product follows one k-block later, so no
+// second x buffer is needed.  Two 256-column accumulators in TMEM let the epilogue of tile i overlap
+// the MMAs of tile i+1.
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -32,14 +35,16 @@ namespace {
 constexpr int kTM = 128;        // outputs per tile (MMA M)
 constexpr int kTN = 256;        // channels per tile (MMA N)
 constexpr int kBK = 32;         // k-values per stage (one 128-byte swizzle row)
-constexpr int kStages = 2;
+constexpr int kXSlots = 4;      // x tiles in flight (converted in place between the products)
+constexpr int kAhSlots = 4;     // A_hi tiles in flight (held until the third product)
+constexpr int kAlSlots = 2;     // A_lo tiles in flight (released after the second product)
 constexpr int kEpiWarps = 8;    // two per TMEM lane quarter: columns [0,128) and [128,256)
 constexpr int kConvWarps = 4;
-constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kConvWarp0 = kEpiWarps + 2;
+constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kTmaWarpA = kEpiWarps + 2, kConvWarp0 = kEpiWarps + 3;
 constexpr int kThreads = (kConvWarp0 + kConvWarps) * 32;
 constexpr uint32_t kABytes = kTM * kBK * 4;   // 16 KB
 constexpr uint32_t kBBytes = kTN * kBK * 4;   // 32 KB
-constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
+constexpr size_t kSmemBytes = kXSlots * kBBytes + (kAhSlots + kAlSlots) * kABytes + 1024;   // 128 + 64 KB + alignment slack
 
 struct MmaArgs {
   float* y; long long y_stride;
@@ -48,7 +53,6 @@ struct MmaArgs {
   int period, nkb;
   long long adv;                // input samples per `period` tiles
   long long n_tt, n_tiles;
-  int dbg;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(const void* p) {
@@ -83,17 +87,26 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));   // swizzle atoms: 1024-byte aligned
-  __shared__ __align__(8) uint64_t bars[3 * kStages + 4];
+  __shared__ __align__(8) uint64_t bars[4 * kXSlots + 2 * kAhSlots + 2 * kAlSlots + 4];
   __shared__ uint32_t tmem_base_s;
-  uint64_t* full = bars;                     // [stage] TMA landed A_hi, A_lo, X
-  uint64_t* conv = bars + kStages;           // [stage] X_lo written (4 converter warps)
-  uint64_t* empty = bars + 2 * kStages;      // [stage] the MMAs reading the stage have completed
-  uint64_t* acc_full = bars + 3 * kStages;   // [2] accumulator complete
-  uint64_t* acc_empty = acc_full + 2;        // [2] accumulator drained by the 4 epilogue warps
+  uint64_t* full_x = bars;                    // [x slot] TMA landed the x tile
+  uint64_t* mid = full_x + kXSlots;           // [x slot] the products with the raw x tile have completed
+  uint64_t* conv = mid + kXSlots;             // [x slot] x replaced in place by x - trunc(x)
+  uint64_t* empty_x = conv + kXSlots;         // [x slot] the product with X_lo has completed
+  uint64_t* full_ah = empty_x + kXSlots;      // [A_hi slot] TMA landed
+  uint64_t* empty_ah = full_ah + kAhSlots;    // [A_hi slot] all three products have completed
+  uint64_t* full_al = empty_ah + kAhSlots;    // [A_lo slot] TMA landed
+  uint64_t* empty_al = full_al + kAlSlots;    // [A_lo slot] the second product has completed
+  uint64_t* acc_full = empty_al + kAlSlots;   // [2] accumulator complete
+  uint64_t* acc_empty = acc_full + 2;         // [2] accumulator drained by the epilogue warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], kConvWarps); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kXSlots; ++s) {
+      mbar_init(&full_x[s], 1); mbar_init(&mid[s], 1); mbar_init(&conv[s], kConvWarps); mbar_init(&empty_x[s], 1);
+    }
+    for (int s = 0; s < kAhSlots; ++s) { mbar_init(&full_ah[s], 1); mbar_init(&empty_ah[s], 1); }
+    for (int s = 0; s < kAlSlots; ++s) { mbar_init(&full_al[s], 1); mbar_init(&empty_al[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     fence_mbar_init();
   }
@@ -107,16 +120,14 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  auto stage_ptr = [&](int s, int which) -> unsigned char* {   // 0: A_hi, 1: A_lo, 2: X, 3: X_lo
-    unsigned char* base = smem + static_cast<size_t>(s) * kStageBytes;
-    return which < 2 ? base + which * kABytes : base + 2 * kABytes + (which - 2) * kBBytes;
-  };
+  auto x_ptr = [&](int s) -> unsigned char* { return smem + static_cast<size_t>(s) * kBBytes; };
+  auto ah_ptr = [&](int s) -> unsigned char* { return smem + static_cast<size_t>(kXSlots) * kBBytes + static_cast<size_t>(s) * kABytes; };
+  auto al_ptr = [&](int s) -> unsigned char* { return ah_ptr(kAhSlots) + static_cast<size_t>(s) * kABytes; };
   const long long first = blockIdx.x, step = gridDim.x;
 
   if (warp == kTmaWarp) {
-    // ---------------- TMA producer ----------------
+    // ---------------- TMA producer, x tiles (HBM latency: kXSlots deep) ----------------
     if (lane == 0) {
-      tma_prefetch_desc(&tm_a);
       tma_prefetch_desc(&tm_x);
       uint32_t it = 0;
       for (long long tile = first; tile < a.n_tiles; tile += step) {
@@ -124,15 +135,29 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int p = static_cast<int>(tt % a.period);
         const long long lo = a.lo[p] + (tt / a.period) * a.adv;
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-          const int s = it % kStages;
-          if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1);
-          mbar_expect_tx(&full[s], ((a.dbg & 2) ? 0 : 2 * kABytes) + kBBytes);
-          if (!(a.dbg & 2)) {
-            tma_load_2d(stage_ptr(s, 0), &tm_a, kb * kBK, (2 * p) * kTM, &full[s]);
-            tma_load_2d(stage_ptr(s, 1), &tm_a, kb * kBK, (2 * p + 1) * kTM, &full[s]);
-          }
-          if (a.dbg & 1) tma_load_2d(stage_ptr(s, 2), &tm_x, kb * kBK, 0, &full[s]);
-          else tma_load_2d(stage_ptr(s, 2), &tm_x, static_cast<int>(lo) + kb * kBK, static_cast<int>(ct) * kTN, &full[s]);
+          const int s = it % kXSlots;
+          if (it >= kXSlots) mbar_wait(&empty_x[s], ((it / kXSlots) - 1) & 1);
+          mbar_expect_tx(&full_x[s], kBBytes);
+          tma_load_2d(x_ptr(s), &tm_x, static_cast<int>(lo) + kb * kBK, static_cast<int>(ct) * kTN, &full_x[s]);
+        }
+      }
+    }
+  } else if (warp == kTmaWarpA) {
+    // ---------------- TMA producer, tap matrices (L2 resident: kASlots deep) ----------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_a);
+      uint32_t it = 0;
+      for (long long tile = first; tile < a.n_tiles; tile += step) {
+        const long long tt = tile % a.n_tt;
+        const int p = static_cast<int>(tt % a.period);
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int sh = it % kAhSlots, sl = it % kAlSlots;
+          if (it >= kAhSlots) mbar_wait(&empty_ah[sh], ((it / kAhSlots) - 1) & 1);
+          mbar_expect_tx(&full_ah[sh], kABytes);
+          tma_load_2d(ah_ptr(sh), &tm_a, kb * kBK, (2 * p) * kTM, &full_ah[sh]);
+          if (it >= kAlSlots) mbar_wait(&empty_al[sl], ((it / kAlSlots) - 1) & 1);
+          mbar_expect_tx(&full_al[sl], kABytes);
+          tma_load_2d(al_ptr(sl), &tm_a, kb * kBK, (2 * p + 1) * kTM, &full_al[sl]);
         }
       }
     }
@@ -141,55 +166,67 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       // D fp32, A/B tf32, both K-major, N = 256, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kTN >> 3) << 17) | (uint32_t(kTM >> 4) << 24);
+      // third product of k-block `j` (deferred one step so the in-place conversion of its x tile overlaps
+      // the first two products of the next k-block)
+      auto finish = [&](uint32_t j, uint32_t d, bool last_of_tile, int b) {
+        const int sx = j % kXSlots, sh = j % kAhSlots;
+        mbar_wait(&conv[sx], (j / kXSlots) & 1);
+        tc_fence_after();
+        const uint64_t dah = umma_desc_sw128(ah_ptr(sh)), dxl = umma_desc_sw128(x_ptr(sx));
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, dah + 2 * k, dxl + 2 * k, idesc, 1u);
+        umma_commit(&empty_x[sx]);
+        umma_commit(&empty_ah[sh]);
+        if (last_of_tile) umma_commit(&acc_full[b]);
+      };
       uint32_t it = 0, ti = 0;
+      uint32_t prev_d = 0;
+      int prev_b = 0;
+      bool have_prev = false, prev_last = false;
       for (long long tile = first; tile < a.n_tiles; tile += step, ++ti) {
         const int b = ti & 1;
         if (ti >= 2) mbar_wait(&acc_empty[b], ((ti >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem + b * kTN;
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);
+          const int sx = it % kXSlots, sh = it % kAhSlots, sl = it % kAlSlots;
+          mbar_wait(&full_ah[sh], (it / kAhSlots) & 1);
+          mbar_wait(&full_al[sl], (it / kAlSlots) & 1);
+          mbar_wait(&full_x[sx], (it / kXSlots) & 1);
           tc_fence_after();
-          const uint64_t dah = umma_desc_sw128(stage_ptr(s, 0)), dal = umma_desc_sw128(stage_ptr(s, 1));
-          const uint64_t dx = umma_desc_sw128(stage_ptr(s, 2)), dxl = umma_desc_sw128(stage_ptr(s, 3));
-          // the two products with the raw x tile start as soon as TMA has landed; only the third
-          // needs the converters' X_lo, which keeps them off the critical path
+          const uint64_t dah = umma_desc_sw128(ah_ptr(sh)), dal = umma_desc_sw128(al_ptr(sl));
+          const uint64_t dx = umma_desc_sw128(x_ptr(sx));
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             umma_tf32(d, dah + 2 * k, dx + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            if (!(a.dbg & 4)) umma_tf32(d, dal + 2 * k, dx + 2 * k, idesc, 1u);
+            umma_tf32(d, dal + 2 * k, dx + 2 * k, idesc, 1u);
           }
-          mbar_wait(&conv[s], ph);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < kBK / 8; ++k)
-            if (!(a.dbg & 4)) umma_tf32(d, dah + 2 * k, dxl + 2 * k, idesc, 1u);
-          umma_commit(&empty[s]);
+          umma_commit(&mid[sx]);
+          umma_commit(&empty_al[sl]);
+          if (have_prev) finish(it - 1, prev_d, prev_last, prev_b);
+          have_prev = true; prev_d = d; prev_b = b; prev_last = (kb == a.nkb - 1);
         }
-        umma_commit(&acc_full[b]);
       }
+      if (have_prev) finish(it - 1, prev_d, prev_last, prev_b);
     }
   } else if (warp >= kConvWarp0) {
-    // ---------------- converters: X_lo = x - trunc_tf32(x), same (swizzled) position ----------------
-    const int ctid = threadIdx.x - kConvWarp0 * 32;   // 0 .. 32*kConvWarps-1
+    // ---------------- converters: x -> x - trunc_tf32(x) in place, once the raw tile has been consumed ----------------
+    const int ctid = threadIdx.x - kConvWarp0 * 32;
     uint32_t it = 0;
     for (long long tile = first; tile < a.n_tiles; tile += step) {
       for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-        const int s = it % kStages;
-        mbar_wait(&full[s], (it / kStages) & 1);
-        const float4* src = reinterpret_cast<const float4*>(stage_ptr(s, 2));
-        float4* dst = reinterpret_cast<float4*>(stage_ptr(s, 3));
+        const int s = it % kXSlots;
+        mbar_wait(&mid[s], (it / kXSlots) & 1);
+        float4* buf = reinterpret_cast<float4*>(x_ptr(s));
 #pragma unroll 4
         for (int i = ctid; i < static_cast<int>(kBBytes / 16); i += 32 * kConvWarps) {
-          const float4 v = src[i];
+          const float4 v = buf[i];
           float4 r;
           r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
           r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
           r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
           r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          dst[i] = r;
+          buf[i] = r;
         }
         fence_proxy_async();
         __syncwarp();
@@ -208,7 +245,7 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(&acc_full[b], (ti >> 1) & 1);
       tc_fence_after();
       const long long m = tt * kTM + quarter * 32 + lane;
-      const bool m_ok = (m < a.n_out) && !(a.dbg & 8);
+      const bool m_ok = m < a.n_out;
       const long long c_first = ct * kTN + half * (kTN / 2);
       const bool all_channels = c_first + kTN / 2 <= a.channels;
       float* p = a.y + c_first * a.y_stride + m;
@@ -309,7 +346,7 @@ bool src_mma_usable(const SrcMmaPlan& mp, const float* x, int64_t xs, int64_t ch
   const int64_t padded = ceil_div(channels, kTN) * kTN;
   if (4 * channels < 3 * padded && getenv("DSPB200_SRC_FORCE_MMA") == nullptr) return false;
   return mp.ok && reinterpret_cast<uintptr_t>(x) % 16 == 0 && xs % 4 == 0 && n_in >= 128 &&
-         kStages * kStageBytes + 1024 <= static_cast<size_t>(max_smem_optin());
+         kSmemBytes <= static_cast<size_t>(max_smem_optin());
 }
 
 int src_mma_run(const SrcMmaPlan& mp, const float* x, int64_t xs, float* y, int64_t ys, int64_t channels,
@@ -327,8 +364,7 @@ int src_mma_run(const SrcMmaPlan& mp, const float* x, int64_t xs, float* y, int6
   a.lo = mp.d_lo; a.period = mp.period; a.nkb = mp.kpad / kBK; a.adv = mp.adv;
   a.n_tt = ceil_div(n_out, kTM);
   a.n_tiles = a.n_tt * ceil_div(channels, kTN);
-  a.dbg = getenv("DSPB200_SRC_MMA_DBG") ? atoi(getenv("DSPB200_SRC_MMA_DBG")) : 0;
-  const size_t smem = kStages * kStageBytes + 1024;
+  const size_t smem = kSmemBytes;
   DSP_CUDA(cudaFuncSetAttribute(src_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t sms = sm_count();
   const int grid = static_cast<int>(a.n_tiles < sms ? a.n_tiles : sms);
