@@ -217,16 +217,19 @@ src_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int kb = 0; kb < a.nkb; ++kb, ++it) {
         const int s = it % kXSlots;
         mbar_wait(&mid[s], (it / kXSlots) & 1);
-        float4* buf = reinterpret_cast<float4*>(x_ptr(s));
-#pragma unroll 4
-        for (int i = ctid; i < static_cast<int>(kBBytes / 16); i += 32 * kConvWarps) {
-          const float4 v = buf[i];
+        float4* buf = reinterpret_cast<float4*>(x_ptr(s)) + ctid;
+        constexpr int kPer = static_cast<int>(kBBytes / 16) / (32 * kConvWarps);   // 16-byte pieces per thread
+        float4 v[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) v[i] = buf[i * 32 * kConvWarps];            // all loads in flight at once
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
           float4 r;
-          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          buf[i] = r;
+          r.x = v[i].x - __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+          r.y = v[i].y - __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+          r.z = v[i].z - __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+          r.w = v[i].w - __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+          buf[i * 32 * kConvWarps] = r;
         }
         fence_proxy_async();
         __syncwarp();
