@@ -107,14 +107,6 @@ int dspb200_src_run_f64(const dspb200_src_plan* plan, const double* x, int64_t x
  * 2 = tensor (fp32 only: banded-Toeplitz GEMM on tcgen05, 3-term TF32 split). */
 int dspb200_src_plan_kernel_kind(const dspb200_src_plan* plan, int64_t channels, int64_t n_in,
                                  int64_t x_stride, int* kind);
-/* Test hooks: the same transform forced onto the generic (one thread per output) kernel
- * or onto the tiled FFMA kernel, whatever the shape would normally select. */
-int dspb200_src_run_generic_f32(const dspb200_src_plan* plan, const float* x, int64_t x_stride,
-                                float* y, int64_t y_stride, int64_t channels, int64_t n_in, void* stream);
-int dspb200_src_run_generic_f64(const dspb200_src_plan* plan, const double* x, int64_t x_stride,
-                                double* y, int64_t y_stride, int64_t channels, int64_t n_in, void* stream);
-int dspb200_src_run_tiled_f32(const dspb200_src_plan* plan, const float* x, int64_t x_stride,
-                              float* y, int64_t y_stride, int64_t channels, int64_t n_in, void* stream);
 /* Host buffers, dense [channels, n_in] -> [channels, n_out]. */
 int dspb200_src_host_f32(int L, int M, const float* x, int64_t channels, int64_t n_in, float* y,
                          int64_t y_capacity_per_channel, int64_t* n_out);
