@@ -23,6 +23,7 @@
 // sample (6 zero-state + 2 correction), i.e. ~50 FMA/sample for six sections.
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -479,6 +480,11 @@ struct dspb200_eq_plan {
   int clip;
   int device;
   std::vector<dspb200::Section> sections;
+  // tensor-core form (eq_mma.cu): tables built on first use, on the device current at that time
+  std::mutex mma_mu;
+  int mma_state = 0;   // 0 not tried, 1 built, -1 not available
+  int mma_device = -1;
+  dspb200::LtiMmaPlan mma;
 };
 
 namespace dspb200 {
@@ -637,6 +643,30 @@ static int dispatch_ns(int ns, const Section* sec, bool clip, const T* x, int64_
   }
 }
 
+// Would a run of this shape use the tensor-core form (eq_mma.cu)?  Builds the plan's tables on first use.
+static int eq_mma_ready(const dspb200_eq_plan* plan, int64_t xs, int64_t channels, int64_t n, bool& tensor) {
+  tensor = false;
+  const int total = static_cast<int>(plan->sections.size());
+  if (plan->dtype != DSPB200_F32 || total < 1 || total > kLtiMaxStates / 2 || getenv("DSPB200_EQ_NO_MMA") != nullptr)
+    return DSPB200_OK;
+  for (const Section& sc : plan->sections)
+    if (!sc.complex_poles) return DSPB200_OK;
+  int dev = 0;
+  DSP_CUDA(cudaGetDevice(&dev));
+  dspb200_eq_plan* mp = const_cast<dspb200_eq_plan*>(plan);
+  {
+    std::lock_guard<std::mutex> lk(mp->mma_mu);
+    if (mp->mma_state == 0) {
+      DSP_TRY(lti_mma_build_eq(mp->sections.data(), total, mp->mma));
+      mp->mma_state = mp->mma.ok ? 1 : -1;
+      mp->mma_device = dev;
+    }
+    if (mp->mma_state != 1 || mp->mma_device != dev) return DSPB200_OK;
+  }
+  tensor = lti_mma_usable(plan->mma, nullptr, xs, channels, n);
+  return DSPB200_OK;
+}
+
 template <typename T>
 int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs, int64_t channels,
            int64_t n, cudaStream_t stream) {
@@ -650,6 +680,15 @@ int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs
   const int total = static_cast<int>(plan->sections.size());
   if (total == 0)
     return launch_pass<T, 0, true>(nullptr, plan->clip != 0, x, xs, z, zs, channels, n, stream);
+  if (sizeof(T) == 4) {
+    bool tensor = false;
+    DSP_TRY(eq_mma_ready(plan, xs, channels, n, tensor));
+    if (tensor && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+      const int rc = lti_mma_run(plan->mma, reinterpret_cast<const float*>(x), xs, reinterpret_cast<float*>(z), zs,
+                                 channels, n, n, plan->clip != 0, stream);
+      if (rc != kLtiNoScratch) return rc;
+    }
+  }
   const T* src = x;
   int64_t src_stride = xs;
   for (int first = 0; first < total; first += kEqPassSections) {
@@ -763,7 +802,18 @@ int dspb200_eq_plan_create_bands(double fs, const double gains_db[DSPB200_EQ_BAN
 }
 
 int dspb200_eq_plan_destroy(dspb200_eq_plan* plan) {
+  if (plan && plan->mma_state == 1) lti_mma_free(plan->mma);
   delete plan;
+  return DSPB200_OK;
+}
+
+int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, int64_t n, int64_t x_stride,
+                                int* kind) {
+  DSP_CHECK(plan != nullptr && kind != nullptr, "NULL argument");
+  DSP_TRY(ensure_device());
+  bool tensor = false;
+  DSP_TRY(eq_mma_ready(plan, x_stride, channels, n, tensor));
+  *kind = tensor ? 1 : 0;
   return DSPB200_OK;
 }
 

@@ -201,6 +201,11 @@ class EqPlan:
         except Exception:      # interpreter shutdown: module globals may already be gone
             pass
 
+    def kernel_kind(self, channels: int, n: int) -> str:
+        k = C.c_int()
+        check(_lib.load().dspb200_eq_plan_kernel_kind(self._h, channels, n, n, C.byref(k)))
+        return {0: "scan", 1: "tensor"}[k.value]
+
     def describe(self) -> np.ndarray:
         n = C.c_int()
         buf = np.zeros((16, 9))
