@@ -644,7 +644,8 @@ static int dispatch_ns(int ns, const Section* sec, bool clip, const T* x, int64_
 }
 
 // Would a run of this shape use the tensor-core form (eq_mma.cu)?  Builds the plan's tables on first use.
-static int eq_mma_ready(const dspb200_eq_plan* plan, int64_t xs, int64_t channels, int64_t n, bool& tensor) {
+static int eq_mma_ready(const dspb200_eq_plan* plan, const float* x, int64_t xs, const float* z, int64_t zs,
+                        int64_t channels, int64_t n, bool& tensor) {
   tensor = false;
   const int total = static_cast<int>(plan->sections.size());
   if (plan->dtype != DSPB200_F32 || total < 1 || total > kLtiMaxStates / 2 || getenv("DSPB200_EQ_NO_MMA") != nullptr)
@@ -663,7 +664,7 @@ static int eq_mma_ready(const dspb200_eq_plan* plan, int64_t xs, int64_t channel
     }
     if (mp->mma_state != 1 || mp->mma_device != dev) return DSPB200_OK;
   }
-  tensor = lti_mma_usable(plan->mma, nullptr, xs, channels, n);
+  tensor = lti_mma_usable(plan->mma, x, xs, z, zs, channels, n);
   return DSPB200_OK;
 }
 
@@ -682,11 +683,10 @@ int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs
     return launch_pass<T, 0, true>(nullptr, plan->clip != 0, x, xs, z, zs, channels, n, stream);
   if (sizeof(T) == 4) {
     bool tensor = false;
-    DSP_TRY(eq_mma_ready(plan, xs, channels, n, tensor));
-    if (tensor && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
-      const int rc = lti_mma_run(plan->mma, reinterpret_cast<const float*>(x), xs, reinterpret_cast<float*>(z), zs,
-                                 channels, n, n, plan->clip != 0, stream);
-      if (rc != kLtiNoScratch) return rc;
+    DSP_TRY(eq_mma_ready(plan, reinterpret_cast<const float*>(x), xs, reinterpret_cast<const float*>(z), zs, channels, n, tensor));
+    if (tensor) {
+      return lti_mma_run(plan->mma, reinterpret_cast<const float*>(x), xs, reinterpret_cast<float*>(z), zs,
+                         channels, n, n, plan->clip != 0, stream);
     }
   }
   const T* src = x;
@@ -812,7 +812,7 @@ int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, i
   DSP_CHECK(plan != nullptr && kind != nullptr, "NULL argument");
   DSP_TRY(ensure_device());
   bool tensor = false;
-  DSP_TRY(eq_mma_ready(plan, x_stride, channels, n, tensor));
+  DSP_TRY(eq_mma_ready(plan, nullptr, x_stride, nullptr, x_stride, channels, n, tensor));
   *kind = tensor ? 1 : 0;
   return DSPB200_OK;
 }

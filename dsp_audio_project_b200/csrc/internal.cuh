@@ -37,7 +37,6 @@ int src_mma_run(const SrcMmaPlan& mp, const float* x, int64_t xs, float* y, int6
                 int64_t n_in, int64_t n_out, cudaStream_t stream);
 // K2 on tcgen05 (eq_mma.cu): the cascade as a chunked linear system.  fp32 only.
 constexpr int kLtiMaxStates = 16;
-constexpr int kLtiNoScratch = -1000;   // lti_mma_run: no memory for the per-tile state records
 struct Section;
 struct LtiMmaPlan {
   int ok = 0;
@@ -46,16 +45,15 @@ struct LtiMmaPlan {
   int kvalid = 0;          // GEMM depth actually multiplied (multiple of 8)
   int states = 0;          // padded to a multiple of 4
   long long adv = 0;       // input samples per `period` chunks
-  float* d_table = nullptr;   // [period][hi, lo][128][kpad]: rows 0..111 outputs, 112.. end states
-  float* d_otab = nullptr;    // [128][16] free response rows
-  int* d_lo = nullptr;        // [period] window start of phase p
+  float* d_table = nullptr;   // [hi, lo, free response][112][kpad]: rows 0..95 outputs, 96.. end states
   float phi[kLtiMaxStates * kLtiMaxStates] = {};   // state transition over one chunk
 };
 void cascade_state_space(const Section* sec, int ns, std::vector<double>& A, std::vector<double>& B,
                          std::vector<double>& C, double& D);
 int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp);
 void lti_mma_free(LtiMmaPlan& mp);
-bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, int64_t channels, int64_t n_in);
+bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs, int64_t channels,
+                    int64_t n_in);
 int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int64_t zs, int64_t channels,
                 int64_t n_in, int64_t n_out, bool clip, cudaStream_t stream);
 int fft_plan_info(const dspb200_fft_plan* plan, int* n_fft, int* dtype);

@@ -375,16 +375,17 @@ def test_src_tensor_core_form_matches_oracle_and_tiled(pk, torch_cuda, L, M, mon
 @pytest.mark.parametrize("gains", [C1_GAINS, (15,) * 6, (3, 0, -2, 0, 0, 5), (0, 0, 0, 0, 0, 12)])
 def test_eq_tensor_core_form_matches_oracle_and_scan(pk, torch_cuda, gains, monkeypatch):
     """fp32 EQ on wide batches runs the cascade as one linear system, 112 samples per tcgen05 GEMM tile,
-    the state carried between tiles by decoupled look-back (csrc/eq_mma.cu).  Forced onto narrow
-    batches here so that many chunks of one channel group are in flight (deep look-back); ragged
-    channel counts, lengths that are not a multiple of the chunk, in place, padded row strides."""
+    the state carried from chunk to chunk in the registers of the thread that owns the channel
+    (csrc/eq_mma.cu).  Forced onto narrow batches here; ragged channel counts, lengths that are not a
+    multiple of the chunk, more channel groups than SMs (a CTA restarts from a zero state), in
+    place, padded and misaligned row strides."""
     torch = torch_cuda
     gd = gains_dict(gains)
     plan = pk.EqPlan.from_gains(48000, gd, np.float32)
     rng = np.random.default_rng(77)
-    for channels, n in ((300, 4412), (256, 112 * 9), (5, 20000), (700, 1124), (3, 1123), (2, 100)):
+    for channels, n in ((300, 4412), (256, 96 * 9), (5, 20000), (128 * 150 + 5, 1124), (3, 1123), (2, 100)):
         monkeypatch.setenv("DSPB200_EQ_FORCE_MMA", "1")
-        assert (plan.kernel_kind(channels, n) == "tensor") == (n % 4 == 0 and n >= 112)
+        assert (plan.kernel_kind(channels, n) == "tensor") == (n % 4 == 0 and n >= 96)
         x = rng.uniform(-0.5, 0.5, (channels, n)).astype(np.float32)
         xt = torch.as_tensor(x, device="cuda")
         z = plan.run(xt)
@@ -406,20 +407,20 @@ def test_eq_tensor_core_form_matches_oracle_and_scan(pk, torch_cuda, gains, monk
         assert torch.equal(out[:, :n], z) and bool((out[:, n:] == 7.0).all())
         monkeypatch.delenv("DSPB200_EQ_FORCE_MMA")
     # the shape rule: wide batches take the tensor form on their own, narrow ones stay on the scan kernel
-    assert plan.kernel_kind(4864, 3000) == "tensor" and plan.kernel_kind(1024, 480000) == "scan"
-    x = torch.rand((4864, 3000), device="cuda", dtype=torch.float32) - 0.5
+    assert plan.kernel_kind(18944, 3000) == "tensor" and plan.kernel_kind(1024, 480000) == "scan"
+    x = torch.rand((18944, 3000), device="cuda", dtype=torch.float32) - 0.5
     z = plan.run(x)
     monkeypatch.setenv("DSPB200_EQ_NO_MMA", "1")
     z_scan = plan.run(x)
     monkeypatch.delenv("DSPB200_EQ_NO_MMA")
     assert float((z - z_scan).abs().max()) <= TOL_F32_EQ
     # real poles (cuts below about -12.04 dB) and fp64 stay on the scan kernel
-    assert pk.EqPlan.from_gains(48000, gains_dict((-15,) * 6), np.float32).kernel_kind(8192, 3000) == "scan"
-    assert pk.EqPlan.from_gains(48000, gd, np.float64).kernel_kind(8192, 3000) == "scan"
+    assert pk.EqPlan.from_gains(48000, gains_dict((-15,) * 6), np.float32).kernel_kind(18944, 3000) == "scan"
+    assert pk.EqPlan.from_gains(48000, gd, np.float64).kernel_kind(18944, 3000) == "scan"
 
 
 def test_eq_tensor_core_form_long_stream(pk, torch_cuda, monkeypatch):
-    """C3's time axis (2.88 M samples = 25 715 chunks) through the tensor form on one channel group."""
+    """C3's time axis (2.88 M samples = 25 715 chunks) through the tensor form on two channel groups."""
     torch = torch_cuda
     n = 2_880_000
     gd = gains_dict((15,) * 6)

@@ -8,7 +8,7 @@ import dsp_audio_project_b200 as pk
 BANDS = ["Sub-Bass", "Bass", "Low Mids", "High Mids", "Presence", "Brilliance"]
 plan = pk.EqPlan.from_gains(48000, dict(zip(BANDS, (6, -3, 4, -6, 3, -9))), np.float32)
 os.environ["DSPB200_EQ_FORCE_MMA"] = "1"
-shapes = [tuple(int(v) for v in s.split("x")) for s in (sys.argv[1:] or ["8192x240000", "16384x120000", "37888x60000"])]
+shapes = [tuple(int(v) for v in s.split("x")) for s in (sys.argv[1:] or ["18944x120000", "37888x60000", "65536x30000"])]
 for ch, n in shapes:
     xt = torch.rand((ch, n), device="cuda", dtype=torch.float32) - 0.5
     out = torch.empty_like(xt)
