@@ -419,6 +419,29 @@ def test_eq_tensor_core_form_matches_oracle_and_scan(pk, torch_cuda, gains, monk
     assert pk.EqPlan.from_gains(48000, gd, np.float64).kernel_kind(18944, 3000) == "scan"
 
 
+@pytest.mark.parametrize("n_sections", [2, 5, 7, 8])
+def test_eq_tensor_core_form_section_counts(pk, torch_cuda, n_sections, monkeypatch):
+    """Every state-count variant of the tensor form (4, 8, 12 and 16 padded states): cascades of 2..8 sections
+    built from explicit band lists (eight sections need both k-blocks of the free-response operand)."""
+    torch = torch_cuda
+    centres = [60.0, 250.0, 700.0, 1500.0, 3200.0, 6000.0, 9000.0, 14000.0][:n_sections]
+    gains = [5.0, -4.0, 7.5, -6.0, 3.0, -9.0, 12.0, -2.5][:n_sections]
+    plan = pk.EqPlan(48000, list(zip(centres, gains)), np.float32)
+    rng = np.random.default_rng(n_sections)
+    channels, n = 261, 9600 + 4
+    x = rng.uniform(-0.4, 0.4, (channels, n)).astype(np.float32)
+    xt = torch.as_tensor(x, device="cuda")
+    monkeypatch.setenv("DSPB200_EQ_FORCE_MMA", "1")
+    assert plan.kernel_kind(channels, n) == "tensor"
+    z = plan.run(xt).cpu().numpy()
+    monkeypatch.delenv("DSPB200_EQ_FORCE_MMA")
+    for c in (0, 130, 260):
+        ref = x[c].astype(np.float64)
+        for fc, g in zip(centres, gains):
+            ref = o.difference_equation(ref, *o.peaking_biquad(fc, 48000, g))
+        assert o.full_scale_err(z[c], np.clip(ref, -1, 1)) <= TOL_F32_EQ, (n_sections, c)
+
+
 def test_eq_tensor_core_form_long_stream(pk, torch_cuda, monkeypatch):
     """C3's time axis (2.88 M samples = 25 715 chunks) through the tensor form on two channel groups."""
     torch = torch_cuda

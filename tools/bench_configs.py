@@ -53,7 +53,7 @@ def report(name, ms, samples, alg_bytes, extra=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--only", default="", help="c4: just the 2^16-point FFT case")
+    ap.add_argument("--only", default="", help="c4: just the 2^16-point FFT case; c3t: just the wide EQ cases")
     args = ap.parse_args()
     if args.only == "c4":
         dev = torch.device("cuda", 0)
@@ -67,6 +67,21 @@ def main():
         return
     dev = torch.device("cuda", 0)
     gen = torch.Generator(device=dev).manual_seed(1)
+    if args.only in ("", "c3t"):
+        # C3 at its full channel count, a twelfth of the time axis per call (63 GB in place): the batch is wide
+        # enough for the tensor-core form of the cascade (csrc/eq_mma.cu); also 18944 = 148 x 128 channels
+        for ch, n in ((65536, 240_000), (18944, 480_000)):
+            x = torch.empty((ch, n), device=dev, dtype=torch.float32)
+            x.uniform_(-0.25, 0.25, generator=gen)
+            for gname, gains in (("C1 gains", GAINS), ("all +15 dB", {k: 15 for k in GAINS})):
+                eq = pkg.EqPlan.from_gains(48000, gains, np.float32)
+                ms = timeit(lambda: eq.run(x, out=x), args.reps)
+                report(f"C3 EQ {ch}x{n} {gname} f32", ms, x.numel(), 8 * x.numel(), {"kernel": eq.kernel_kind(ch, n)})
+                x.uniform_(-0.25, 0.25, generator=gen)
+            del x
+            torch.cuda.empty_cache()
+        if args.only == "c3t":
+            return
     for tdt, ndt, es, tag in ((torch.float32, np.float32, 4, "f32"), (torch.float64, np.float64, 8, "f64")):
         # C2: SRC 160/147, 1024 ch x 441000
         x = torch.rand((1024, 441000), generator=gen, device=dev, dtype=tdt) - 0.5

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (raw page) into a small markdown/JSON table for profiles/.
 
-    python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r1_ncu_full.md [--traffic profiles/traffic.json]
+    python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r1_ncu_full.md [--traffic profiles/traffic.json [--clips N]]
 """
 import csv
 import io
 import json
+import re
 import subprocess
 import sys
 
@@ -28,6 +29,8 @@ KEYS = [
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data pipe (LSU + tensor operand reads) % of peak"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "tensor-core operand reads from smem % of peak"),
 ]
 
 
@@ -58,14 +61,16 @@ def main():
                 return float(v) * m.get(u, 1)
             rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
             wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
-            short = name.split("<")[0].split("::")[-1].replace("void ", "").strip()
+            m = re.search(r"(\w+_kernel)", name)
+            short = m.group(1) if m else name.split("<")[0].split("::")[-1].replace("void ", "").strip()
             traffic[short] = rd + wr
         except Exception:
             pass
     open(out, "w").write("\n".join(lines) + "\n")
     if traffic_path:
+        if len(sys.argv) > 6 and sys.argv[5] == "--clips":
+            traffic["clips_per_launch"] = int(sys.argv[6])
         json.dump(traffic, open(traffic_path, "w"), indent=1)
-    print(open(out).read()[:600])
 
 
 if __name__ == "__main__":
