@@ -24,7 +24,7 @@
 //
 // Warp roles (one persistent CTA per SM): warps 0-3 epilogue (one TMEM lane quarter each), warp 4
 // TMA producer (the coefficient tiles once -- they stay resident in shared memory -- then x tiles
-// through a 7-deep ring), warp 5 MMA issuer, warps 6-9 converters.  Four accumulators let the MMAs run up to
+// through a 5-deep ring), warp 5 MMA issuer, warps 6-7 converters.  Four accumulators let the MMAs run up to
 // three chunks ahead of the epilogue; the only serial link per chunk is
 // accumulator -> state update -> tcgen05.st -> six free-response MMAs of the next chunk.
 //
@@ -33,6 +33,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "design.cuh"
@@ -49,10 +50,11 @@ constexpr int kBK = 32;         // k-values per stage (one 128-byte swizzle row)
 constexpr int kNkb = kRows / kBK;
 constexpr int kXSlots = 5;
 constexpr int kStages = 2;       // staging tiles of the TMA stores
+constexpr int kJobQ = 16;        // job queue depth; no role runs more than ~7 items ahead of the epilogue
 constexpr int kAccs = 4;
 constexpr int kSCol = kAccs * kTNn;           // TMEM columns 448..511: the split start states (A operand of the correction)
 constexpr int kEpiWarps = 4;
-constexpr int kConvWarps = 4;
+constexpr int kConvWarps = 2;      // 8 warps in all: registers are allotted in groups of four warps, 10 warps would cap the kernel at 168
 constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kConvWarp0 = kEpiWarps + 2;
 constexpr int kThreads = (kConvWarp0 + kConvWarps) * 32;
 constexpr uint32_t kTabBytes = kTNn * kBK * 4;   // 14 KB: one k-block of [T; K] (hi or lo) or of O
@@ -64,6 +66,12 @@ struct LtiArgs {
   float* z; long long z_stride;
   long long channels, n_out;
   long long n_tt, n_groups;
+  // work items: (channel group, time slice) pairs, slice-major, handed out by an atomic counter so that a slice only
+  // ever waits for a lower-numbered item, which a running CTA already owns
+  long long n_jobs, chunks_per_job;
+  unsigned* counter;            // job dispenser
+  unsigned* done;               // [n_jobs] 1 once the item's end state is in `xfer`
+  float* xfer;                  // [n_jobs][kS][128] end states handed to the group's next slice
   int clip;
   unsigned long long* prof;     // development: cycles per epilogue phase (NULL = off)
   float phi[kLtiMaxStates * kLtiMaxStates];
@@ -105,6 +113,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ float clip_unit(float y) {   // NaN passes through like np.clip
   float r;
   asm("max.NaN.f32 %0, %1, 0fBF800000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(r) : "f"(y));
@@ -134,7 +150,8 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));   // swizzle atoms: 1024-byte aligned
-  __shared__ __align__(8) uint64_t bars[4 * kXSlots + 2 * kAccs + 2];
+  __shared__ __align__(8) uint64_t bars[4 * kXSlots + 2 * kAccs + 2 + kJobQ];
+  __shared__ long long job_q[kJobQ];
   __shared__ uint32_t tmem_base_s;
   uint64_t* full_x = bars;                    // [x slot] TMA landed the x tile
   uint64_t* mid = full_x + kXSlots;           // [x slot] the products with the raw x tile have completed
@@ -144,6 +161,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint64_t* acc_empty = acc_full + kAccs;     // [acc] accumulator drained by the epilogue warps
   uint64_t* tab_full = acc_empty + kAccs;     // coefficient tiles resident
   uint64_t* s_ready = tab_full + 1;           // the next chunk's start states are in tensor memory
+  uint64_t* job_full = s_ready + 1;           // [queue slot] the dispenser has filled it
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -152,7 +170,8 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     for (int b = 0; b < kAccs; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     mbar_init(tab_full, 1);
-    mbar_init(s_ready, 4);
+    mbar_init(s_ready, kEpiWarps);
+    for (int q = 0; q < kJobQ; ++q) mbar_init(&job_full[q], 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -169,6 +188,21 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   unsigned char* stage0 = x_ptr(kXSlots);                                         // kStages x [128 channels][32 samples], swizzled
   auto tab_ptr = [&](int kb, int hl) -> unsigned char* { return smem + static_cast<size_t>(kb * 2 + hl) * kTabBytes; };
   auto o_ptr = [&](int kb) -> unsigned char* { return smem + static_cast<size_t>(2 * kNkb + kb) * kTabBytes; };
+  // the i-th work item of this CTA (-1: none left); group, slice and chunk range of an item
+  auto next_job = [&](uint32_t i) -> long long {
+    mbar_wait(&job_full[i % kJobQ], (i / kJobQ) & 1);
+    return *reinterpret_cast<volatile long long*>(&job_q[i % kJobQ]);
+  };
+  struct Job { int g, h, t0, t1; };
+  auto job_of = [&](long long j) -> Job {
+    Job r;
+    const int jj = static_cast<int>(j), ng = static_cast<int>(a.n_groups), cpj = static_cast<int>(a.chunks_per_job);
+    r.h = jj / ng;
+    r.g = jj - r.h * ng;
+    r.t0 = r.h * cpj;
+    r.t1 = r.t0 + cpj < static_cast<int>(a.n_tt) ? r.t0 + cpj : static_cast<int>(a.n_tt);
+    return r;
+  };
 
   if (warp == kTmaWarp) {
     // ---------------- TMA producer: coefficient tiles once, then x tiles ----------------
@@ -180,14 +214,21 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int hl = 0; hl < 2; ++hl) tma_load_2d(tab_ptr(kb, hl), &tm_a, kb * kBK, hl * kTNn, tab_full);
       for (int kb = 0; kb < 2; ++kb) tma_load_2d(o_ptr(kb), &tm_a, kb * kBK, 2 * kTNn, tab_full);
       uint32_t it = 0;
-      for (long long g = blockIdx.x; g < a.n_groups; g += gridDim.x)
-        for (long long tt = 0; tt < a.n_tt; ++tt)
+      for (uint32_t ji = 0;; ++ji) {
+        long long j = static_cast<long long>(atomicAdd(a.counter, 1u));
+        if (j >= a.n_jobs) j = -1;
+        *reinterpret_cast<volatile long long*>(&job_q[ji % kJobQ]) = j;
+        mbar_arrive(&job_full[ji % kJobQ]);
+        if (j < 0) break;
+        const Job jb = job_of(j);
+        for (int tt = jb.t0; tt < jb.t1; ++tt)
           for (int kb = 0; kb < kNkb; ++kb, ++it) {
             const int s = it % kXSlots;
             if (it >= kXSlots) mbar_wait(&empty_x[s], ((it / kXSlots) - 1) & 1);
             mbar_expect_tx(&full_x[s], kXBytes);
-            tma_load_2d(x_ptr(s), &tm_x, static_cast<int>(tt * kRows) + kb * kBK, static_cast<int>(g) * kTM, &full_x[s]);
+            tma_load_2d(x_ptr(s), &tm_x, tt * kRows + kb * kBK, jb.g * kTM, &full_x[s]);
           }
+      }
     }
   } else if (warp == kMmaWarp) {
     // ---------------- MMA issuer ----------------
@@ -223,8 +264,11 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t prev_d = 0;
       int prev_b = 0, prev_kb = 0;
       bool have_prev = false, prev_last = false, prev_corr = false;
-      for (long long g = blockIdx.x; g < a.n_groups; g += gridDim.x)
-        for (long long tt = 0; tt < a.n_tt; ++tt, ++ti) {
+      for (uint32_t ji = 0;; ++ji) {
+        const long long j = next_job(ji);
+        if (j < 0) break;
+        const Job jb = job_of(j);
+        for (int tt = jb.t0; tt < jb.t1; ++tt, ++ti) {
           const int b = ti % kAccs;
           if (ti >= kAccs) mbar_wait(&acc_empty[b], ((ti / kAccs) - 1) & 1);
           tc_fence_after();
@@ -242,18 +286,21 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             umma_commit(&mid[sx]);
             if (have_prev) finish(it - 1, prev_kb, prev_d, prev_last, prev_b, prev_corr);
-            have_prev = true; prev_d = d; prev_b = b; prev_kb = kb; prev_last = (kb == kNkb - 1); prev_corr = tt > 0;
+            have_prev = true; prev_d = d; prev_b = b; prev_kb = kb; prev_last = (kb == kNkb - 1); prev_corr = tt > 0;   // chunk 0 starts from a zero state; a later slice's first chunk from the handed-over one
           }
         }
+      }
       if (have_prev) finish(it - 1, prev_kb, prev_d, prev_last, prev_b, prev_corr);
     }
   } else if (warp >= kConvWarp0) {
     // ---------------- converters: x -> x - trunc_tf32(x) in place, once the raw tile has been consumed ----------------
     const int ctid = threadIdx.x - kConvWarp0 * 32;
     uint32_t it = 0;
-    for (long long g = blockIdx.x; g < a.n_groups; g += gridDim.x)
-      for (long long tt = 0; tt < a.n_tt; ++tt)
-        for (int kb = 0; kb < kNkb; ++kb, ++it) {
+    for (uint32_t ji = 0;; ++ji) {
+      const long long j = next_job(ji);
+      if (j < 0) break;
+      const Job jb = job_of(j);
+      for (int n_kb = (jb.t1 - jb.t0) * kNkb; n_kb > 0; --n_kb, ++it) {
           const int s = it % kXSlots;
           mbar_wait(&mid[s], (it / kXSlots) & 1);
           float4* buf = reinterpret_cast<float4*>(x_ptr(s)) + ctid;
@@ -273,17 +320,53 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&conv[s]);
-        }
+      }
+    }
   } else {
     // ---------------- epilogue warps 0-3: thread = TMEM lane = channel ----------------
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     constexpr int kBlocks = kRows / 16;
     uint32_t ti = 0, n_st = 0;
-    for (long long g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
-      float s[kS];
+    // the start state of the coming chunk, split in three TF32 pieces, to tensor memory: [s1 | s2 | s3 | s1]
+    auto hand_over = [&](const float (&s)[kS]) {
 #pragma unroll
-      for (int i = 0; i < kS; ++i) s[i] = 0.f;       // zero initial state per channel (lfilter, dsp_core.py:214)
-      for (long long tt = 0; tt < a.n_tt; ++tt, ++ti) {
+      for (int q = 0; q < kS / 4; ++q) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = 16 * q + j, i = col % kS, piece = col / kS;
+          const float s1 = trunc_tf32(s[i]);
+          const float r1 = s[i] - s1;
+          const float s2 = trunc_tf32(r1);
+          w[j] = __float_as_uint(piece == 1 ? s2 : (piece == 2 ? r1 - s2 : s1));
+        }
+        tmem_st16(lane_base + kSCol + 16 * q, w);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_ready);
+    };
+    for (uint32_t ji = 0;; ++ji) {
+      const long long job = next_job(ji);
+      if (job < 0) break;
+      const Job jb = job_of(job);
+      const int g = jb.g;
+      float s[kS];
+      if (jb.h == 0) {
+#pragma unroll
+        for (int i = 0; i < kS; ++i) s[i] = 0.f;     // zero initial state per channel (lfilter, dsp_core.py:214)
+      } else {
+        // later slice of the group: its start state is the end state of the slice before, finished rounds ago
+        const long long pj = job - a.n_groups;
+        while (ld_acquire(a.done + pj) == 0u) {
+        }
+        const float* r = a.xfer + static_cast<size_t>(pj) * (kS * kTM) + warp * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < kS; ++i) s[i] = __ldcg(r + i * kTM);
+        hand_over(s);
+      }
+      for (int tt = jb.t0; tt < jb.t1; ++tt, ++ti) {
         const int b = ti % kAccs;
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         const bool prof = a.prof && threadIdx.x == 0;
@@ -309,25 +392,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           for (int i = 0; i < kS; ++i) u[i] = __uint_as_float(uu[i]);
           advance_state<kS>(s, a.phi, u);
         }
-        if (tt + 1 < a.n_tt) {
-#pragma unroll
-          for (int q = 0; q < kS / 4; ++q) {
-            uint32_t w[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = 16 * q + j, i = col % kS, piece = col / kS;   // [s1 | s2 | s3 | s1]
-              const float s1 = trunc_tf32(s[i]);
-              const float r1 = s[i] - s1;
-              const float s2 = trunc_tf32(r1);
-              w[j] = __float_as_uint(piece == 1 ? s2 : (piece == 2 ? r1 - s2 : s1));
-            }
-            tmem_st16(lane_base + kSCol + 16 * q, w);
-          }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_ready);
-        }
+        if (tt + 1 < jb.t1) hand_over(s);
         if (prof) t3 = clock64();
         // clip; each thread lays its channel's 32-sample runs into a 128-byte-swizzled staging tile, which goes out
         // as one TMA store of [128 channels x 32 samples] (full lines, clipped at the tensor's edges by the hardware)
@@ -353,7 +418,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           fence_proxy_async();
           epi_bar();
           if (threadIdx.x == 0) {
-            tma_store_2d(&tm_z, stage, static_cast<int>(tt * kRows) + blk * 32, static_cast<int>(g) * kTM);
+            tma_store_2d(&tm_z, stage, tt * kRows + blk * 32, g * kTM);
             tma_store_commit();
           }
         }
@@ -364,6 +429,15 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           atomicAdd(a.prof + 4, static_cast<unsigned long long>(clock64() - t3));    // clip + stores
           atomicAdd(a.prof + 2, 1ull);
         }
+      }
+      if (jb.t1 < static_cast<int>(a.n_tt)) {
+        // the group goes on in a later slice: leave the end state where that slice will pick it up
+        float* r = a.xfer + static_cast<size_t>(job) * (kS * kTM) + warp * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < kS; ++i) __stcg(r + i * kTM, s[i]);
+        __threadfence();
+        epi_bar();
+        if (threadIdx.x == 0) st_release(a.done + job, 1u);
       }
     }
   }
@@ -393,6 +467,8 @@ Mat mat_mul(const Mat& x, const Mat& y, int n) {
     }
   return r;
 }
+
+std::once_flag g_pool_once;
 
 template <int kS>
 int launch(const CUtensorMap& tm_a, const CUtensorMap& tm_x, const CUtensorMap& tm_z, const LtiArgs& a, int grid, cudaStream_t stream) {
@@ -528,9 +604,10 @@ bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const floa
   if (kSmemBytes + 2048 > static_cast<size_t>(max_smem_optin())) return false;
   if (getenv("DSPB200_EQ_FORCE_MMA") != nullptr) return true;
   // a CTA walks a group of 128 channels through time: the form pays once the groups fill at least 80 % of the
-  // SMs in every round (about 15k channels on 148 SMs); narrower batches stay on the FFMA scan kernel
+  // SMs (about 15k channels on 148 SMs); narrower batches stay on the FFMA scan kernel.  With more groups than
+  // SMs the time axis is cut in slices to even out the rounds (lti_mma_run).
   const int64_t groups = ceil_div(channels, kTM), sms = sm_count();
-  return 5 * groups >= 4 * ceil_div(groups, sms) * sms;
+  return 5 * groups >= 4 * sms;
 }
 
 int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int64_t zs, int64_t channels,
@@ -550,11 +627,50 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
   a.z = z; a.z_stride = zs; a.channels = channels; a.n_out = n_out;
   a.n_tt = ceil_div(n_out, kRows);
   a.n_groups = ceil_div(channels, kTM);
-  DSP_CHECK(n_in < (1ll << 31) - 256 && channels < (1ll << 31) - 256, "shape too large for the tensor-core EQ kernel");
+  DSP_CHECK(n_in < (1ll << 31) - 256 && channels < (1ll << 31) - 256 && n_out < (1ll << 31) - 256,
+            "shape too large for the tensor-core EQ kernel");
   a.clip = clip ? 1 : 0;
   memcpy(a.phi, mp.phi, sizeof(a.phi));
   const int64_t sms = sm_count();
-  const int grid = static_cast<int>(a.n_groups < sms ? a.n_groups : sms);
+  // time slices per group: with at least one group per SM a slice's predecessor ran a whole round earlier, so its end
+  // state is waiting in memory; the smallest count that fills >= 95 % of the last round (or the best one up to 16)
+  int64_t slices = 1;
+  if (a.n_groups > sms) {
+    double best = 0.0;
+    for (int64_t h = 1; h <= 16 && ceil_div(a.n_tt, h) >= 8; ++h) {
+      const int64_t jobs = a.n_groups * ceil_div(a.n_tt, ceil_div(a.n_tt, h));
+      const double eff = static_cast<double>(jobs) / static_cast<double>(ceil_div(jobs, sms) * sms);
+      if (eff > best + 1e-9) { best = eff; slices = h; }
+      if (eff >= 0.95) break;
+    }
+  }
+  if (const char* e = getenv("DSPB200_EQ_SLICES")) {   // development: force the slice count
+    const long v = atol(e);
+    if (v >= 1 && v <= a.n_tt) slices = v;
+  }
+  a.chunks_per_job = ceil_div(a.n_tt, slices);
+  slices = ceil_div(a.n_tt, a.chunks_per_job);
+  a.n_jobs = a.n_groups * slices;
+  DSP_CHECK(a.n_jobs < (1ll << 31), "shape too large for the tensor-core EQ kernel");
+  const int grid = static_cast<int>(a.n_jobs < sms ? a.n_jobs : sms);
+  // stream-ordered scratch: the job counter, one flag per work item and, when sliced, the handed-over end states
+  std::call_once(g_pool_once, [] {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  });
+  const size_t flag_bytes = static_cast<size_t>(round_up((a.n_jobs + 1) * static_cast<int64_t>(sizeof(unsigned)), 256));
+  const size_t xfer_bytes = slices > 1 ? static_cast<size_t>(a.n_jobs) * mp.states * kTM * sizeof(float) : 0;
+  unsigned char* scratch = nullptr;
+  DSP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), flag_bytes + xfer_bytes, stream));
+  DSP_CUDA(cudaMemsetAsync(scratch, 0, flag_bytes, stream));
+  a.counter = reinterpret_cast<unsigned*>(scratch);
+  a.done = a.counter + 1;
+  a.xfer = reinterpret_cast<float*>(scratch + flag_bytes);
   unsigned long long* prof = nullptr;
   if (getenv("DSPB200_LTI_PROF") != nullptr) {
     cudaMalloc(reinterpret_cast<void**>(&prof), 8 * sizeof(unsigned long long));
@@ -569,14 +685,15 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
     case 16: rc = launch<16>(tm_a, tm_x, tm_z, a, grid, stream); break;
     default: rc = fail(DSPB200_ERR_INVALID, "internal: bad state count %d", mp.states);
   }
+  cudaFreeAsync(scratch, stream);
   if (prof) {
     unsigned long long h[8];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(prof);
     const double nt = h[2] ? static_cast<double>(h[2]) : 1.0;
-    fprintf(stderr, "lti_mma: %d CTAs; epilogue cycles per tile: waiting for the accumulator %.0f, tensor memory -> registers %.0f, state hand-over %.0f, clip + stores %.0f\n",
-            grid, h[0] / nt, h[1] / nt, h[3] / nt, h[4] / nt);
+    fprintf(stderr, "lti_mma: %d CTAs, %lld groups x %lld slices; epilogue cycles per tile: waiting for the accumulator %.0f, tensor memory -> registers %.0f, state hand-over %.0f, clip + stores %.0f\n",
+            grid, static_cast<long long>(a.n_groups), static_cast<long long>(slices), h[0] / nt, h[1] / nt, h[3] / nt, h[4] / nt);
   }
   return rc;
 }

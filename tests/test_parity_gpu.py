@@ -442,6 +442,43 @@ def test_eq_tensor_core_form_section_counts(pk, torch_cuda, n_sections, monkeypa
         assert o.full_scale_err(z[c], np.clip(ref, -1, 1)) <= TOL_F32_EQ, (n_sections, c)
 
 
+@pytest.mark.parametrize("slices", [2, 5, 13])
+def test_eq_tensor_core_form_time_slices(pk, torch_cuda, slices, monkeypatch):
+    """With more channel groups than SMs the tensor form cuts the time axis into slices to even out the rounds;
+    a later slice starts from the end state its predecessor left in memory.  Forced here on a small batch (the
+    predecessor is then still running when the successor asks for its state)."""
+    torch = torch_cuda
+    gd = gains_dict((15,) * 6)
+    plan = pk.EqPlan.from_gains(48000, gd, np.float32)
+    rng = np.random.default_rng(slices)
+    channels, n = 389, 96 * 61 + 40
+    x = rng.uniform(-0.25, 0.25, (channels, n)).astype(np.float32)
+    xt = torch.as_tensor(x, device="cuda")
+    monkeypatch.setenv("DSPB200_EQ_FORCE_MMA", "1")
+    z1 = plan.run(xt)
+    monkeypatch.setenv("DSPB200_EQ_SLICES", str(slices))
+    z = plan.run(xt)
+    monkeypatch.delenv("DSPB200_EQ_SLICES")
+    monkeypatch.delenv("DSPB200_EQ_FORCE_MMA")
+    assert float((z - z1).abs().max()) <= 2e-6            # same arithmetic up to the fp32 round trip of the state
+    pick = [0, 200, 388]
+    ref = np.stack([o.equalizer(x[c].astype(np.float64), 48000, gd) for c in pick])
+    assert o.full_scale_err(z.cpu().numpy()[pick], ref) <= TOL_F32_EQ
+
+
+def test_eq_tensor_core_form_more_groups_than_sms(pk, torch_cuda, monkeypatch):
+    """150 x 128 channels on 148 SMs: the slice count is chosen by the library; against the scan kernel."""
+    torch = torch_cuda
+    plan = pk.EqPlan.from_gains(48000, gains_dict(C1_GAINS), np.float32)
+    x = torch.rand((150 * 128, 9600), device="cuda", dtype=torch.float32) - 0.5
+    assert plan.kernel_kind(150 * 128, 9600) == "tensor"
+    z = plan.run(x)
+    monkeypatch.setenv("DSPB200_EQ_NO_MMA", "1")
+    z_scan = plan.run(x)
+    monkeypatch.delenv("DSPB200_EQ_NO_MMA")
+    assert float((z - z_scan).abs().max()) <= TOL_F32_EQ
+
+
 def test_eq_tensor_core_form_long_stream(pk, torch_cuda, monkeypatch):
     """C3's time axis (2.88 M samples = 25 715 chunks) through the tensor form on two channel groups."""
     torch = torch_cuda
