@@ -23,6 +23,7 @@
 // sample (6 zero-state + 2 correction), i.e. ~50 FMA/sample for six sections.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -650,8 +651,6 @@ static int eq_mma_ready(const dspb200_eq_plan* plan, const float* x, int64_t xs,
   const int total = static_cast<int>(plan->sections.size());
   if (plan->dtype != DSPB200_F32 || total < 1 || total > kLtiMaxStates / 2 || getenv("DSPB200_EQ_NO_MMA") != nullptr)
     return DSPB200_OK;
-  for (const Section& sc : plan->sections)
-    if (!sc.complex_poles) return DSPB200_OK;
   int dev = 0;
   DSP_CUDA(cudaGetDevice(&dev));
   dspb200_eq_plan* mp = const_cast<dspb200_eq_plan*>(plan);
@@ -814,6 +813,20 @@ int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, i
   bool tensor = false;
   DSP_TRY(eq_mma_ready(plan, nullptr, x_stride, nullptr, x_stride, channels, n, tensor));
   *kind = tensor ? 1 : 0;
+  return DSPB200_OK;
+}
+
+int dspb200_eq_plan_chunk_system(const dspb200_eq_plan* plan, int* rows, int* states, double* tk, double* o,
+                                 double* phi) {
+  DSP_CHECK(plan != nullptr && rows != nullptr && states != nullptr, "NULL argument");
+  LtiChunkSystem cs;
+  DSP_TRY(lti_chunk_system(plan->sections.data(), static_cast<int>(plan->sections.size()), cs));
+  *rows = cs.rows;
+  *states = cs.states;
+  if (cs.rows == 0) return DSPB200_OK;
+  if (tk) memcpy(tk, cs.tk.data(), cs.tk.size() * sizeof(double));
+  if (o) memcpy(o, cs.o.data(), cs.o.size() * sizeof(double));
+  if (phi) memcpy(phi, cs.phi.data(), cs.phi.size() * sizeof(double));
   return DSPB200_OK;
 }
 

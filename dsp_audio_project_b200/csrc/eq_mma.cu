@@ -506,8 +506,10 @@ void cascade_state_space(const Section* sec, int ns, std::vector<double>& A, std
   }
 }
 
-int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp) {
-  mp = LtiMmaPlan{};
+// The chunk system of a cascade in float64 (host only): z = T x + O s, s' = Phi s + K x over kRows samples, states
+// rescaled to unit row norms of K so that every state row of the GEMM is computed at full relative precision.
+int lti_chunk_system(const Section* sec, int ns, LtiChunkSystem& cs) {
+  cs = LtiChunkSystem{};
   if (ns < 1 || 2 * ns > kLtiMaxStates) return DSPB200_OK;
   const int n = 2 * ns;
   std::vector<double> A, B, C;
@@ -545,7 +547,6 @@ int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp) {
     for (int j = 0; j < n; ++j) s += static_cast<long double>(cak[m - 1][static_cast<size_t>(j)]) * B[static_cast<size_t>(j)];
     h[m] = static_cast<double>(s);
   }
-  // balance the states: unit row norms of K (the GEMM rows), so every state is computed at full relative precision
   std::vector<double> scale(static_cast<size_t>(n), 1.0);
   for (int i = 0; i < n; ++i) {
     long double ss = 0.0L;
@@ -553,33 +554,53 @@ int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp) {
     const double nrm = std::sqrt(static_cast<double>(ss));
     if (nrm > 0.0 && std::isfinite(nrm)) scale[static_cast<size_t>(i)] = 1.0 / nrm;
   }
+  cs.rows = kRows;
+  cs.states = n;
+  cs.tk.assign(static_cast<size_t>(kRows + kLtiMaxStates) * kRows, 0.0);
+  cs.o.assign(static_cast<size_t>(kRows) * kLtiMaxStates, 0.0);
+  cs.phi.assign(static_cast<size_t>(kLtiMaxStates) * kLtiMaxStates, 0.0);
+  for (int r = 0; r < kRows; ++r)
+    for (int k = 0; k <= r; ++k) cs.tk[static_cast<size_t>(r) * kRows + k] = h[r - k];
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < kRows; ++k)
+      cs.tk[static_cast<size_t>(kRows + i) * kRows + k] = scale[static_cast<size_t>(i)] * akb[kRows - 1 - k][static_cast<size_t>(i)];
+  for (int r = 0; r < kRows; ++r)
+    for (int i = 0; i < n; ++i) cs.o[static_cast<size_t>(r) * kLtiMaxStates + i] = cak[r][static_cast<size_t>(i)] / scale[static_cast<size_t>(i)];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      cs.phi[static_cast<size_t>(i) * kLtiMaxStates + j] = phi[static_cast<size_t>(i) * n + j] * scale[static_cast<size_t>(i)] / scale[static_cast<size_t>(j)];
+  return DSPB200_OK;
+}
+
+int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp) {
+  mp = LtiMmaPlan{};
+  LtiChunkSystem cs;
+  DSP_TRY(lti_chunk_system(sec, ns, cs));
+  if (cs.rows != kRows) return DSPB200_OK;
+  const int n = cs.states;
   const int kpad = kRows;
   const int ks = (n + 3) / 4 * 4;                     // states padded to a multiple of 4
   // three sections of kTNn rows: [T; K] rounded to TF32, its remainder, and the free-response operand
   std::vector<float> tab(static_cast<size_t>(3) * kTNn * kpad, 0.f);
-  auto put = [&](int r, int k, double val) {
-    const float v = static_cast<float>(val);
-    const float hi = round_tf32(v);
-    tab[(static_cast<size_t>(0) * kTNn + r) * kpad + k] = hi;
-    tab[(static_cast<size_t>(1) * kTNn + r) * kpad + k] = v - hi;
-  };
-  for (int r = 0; r < kRows; ++r)
-    for (int k = 0; k <= r; ++k) put(r, k, h[r - k]);
-  for (int i = 0; i < n; ++i)
-    for (int k = 0; k < kRows; ++k) put(kRows + i, k, scale[static_cast<size_t>(i)] * akb[kRows - 1 - k][static_cast<size_t>(i)]);
+  for (int r = 0; r < kRows + n; ++r)
+    for (int k = 0; k < kRows; ++k) {
+      const float v = static_cast<float>(cs.tk[static_cast<size_t>(r) * kRows + k]);
+      const float hi = round_tf32(v);
+      tab[(static_cast<size_t>(0) * kTNn + r) * kpad + k] = hi;
+      tab[(static_cast<size_t>(1) * kTNn + r) * kpad + k] = v - hi;
+    }
   // z += [s1 | s2 | s3 | s1] . [O_hi | O_hi | O_hi | O_lo]^T  (s = s1 + s2 + s3 in TF32 pieces, O = C A^r in the scaled basis);
   // rows kRows.. stay zero: the end-state columns of the accumulator take no free response
   for (int r = 0; r < kRows; ++r)
     for (int i = 0; i < n; ++i) {
-      const float v = static_cast<float>(cak[r][static_cast<size_t>(i)] / scale[static_cast<size_t>(i)]);
+      const float v = static_cast<float>(cs.o[static_cast<size_t>(r) * kLtiMaxStates + i]);
       const float hi = round_tf32(v);
       float* row = &tab[(static_cast<size_t>(2) * kTNn + r) * kpad];
       row[i] = hi; row[ks + i] = hi; row[2 * ks + i] = hi; row[3 * ks + i] = v - hi;
     }
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < n; ++j)
-      mp.phi[i * kLtiMaxStates + j] = static_cast<float>(phi[static_cast<size_t>(i) * n + j] * scale[static_cast<size_t>(i)] / scale[static_cast<size_t>(j)]);
+  for (int i = 0; i < kLtiMaxStates * kLtiMaxStates; ++i) mp.phi[i] = static_cast<float>(cs.phi[static_cast<size_t>(i)]);
   for (float v : tab) if (!std::isfinite(v)) return DSPB200_OK;
+  for (float v : mp.phi) if (!std::isfinite(v)) return DSPB200_OK;
   DSP_CUDA(cudaMalloc(reinterpret_cast<void**>(&mp.d_table), tab.size() * sizeof(float)));
   DSP_CUDA(cudaMemcpy(mp.d_table, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
   mp.period = 1;

@@ -48,6 +48,13 @@ struct LtiMmaPlan {
   float* d_table = nullptr;   // [hi, lo, free response][112][kpad]: rows 0..95 outputs, 96.. end states
   float phi[kLtiMaxStates * kLtiMaxStates] = {};   // state transition over one chunk
 };
+// z = T x + O s, s' = Phi s + K x over `rows` samples (float64, host): tk [(rows + 16) x rows] = [T; K],
+// o [rows x 16], phi [16 x 16]; unused state rows/columns are zero.
+struct LtiChunkSystem {
+  int rows = 0, states = 0;
+  std::vector<double> tk, o, phi;
+};
+int lti_chunk_system(const Section* sec, int ns, LtiChunkSystem& cs);
 void cascade_state_space(const Section* sec, int ns, std::vector<double>& A, std::vector<double>& B,
                          std::vector<double>& C, double& D);
 int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp);

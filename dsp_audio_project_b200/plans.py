@@ -206,6 +206,21 @@ class EqPlan:
         check(_lib.load().dspb200_eq_plan_kernel_kind(self._h, channels, n, n, C.byref(k)))
         return {0: "scan", 1: "tensor"}[k.value]
 
+    def chunk_system(self):
+        """(T, K, O, Phi) of the chunk system the tensor-core form multiplies, float64, host only:
+        z = T x + O s, s' = Phi s + K x over T.shape[0] samples.  None when the plan has no tensor form."""
+        rows, states = C.c_int(), C.c_int()
+        lib = _lib.load()
+        check(lib.dspb200_eq_plan_chunk_system(self._h, C.byref(rows), C.byref(states), None, None, None))
+        if rows.value == 0:
+            return None
+        r, n = rows.value, states.value
+        tk, o, phi = np.zeros((r + 16, r)), np.zeros((r, 16)), np.zeros((16, 16))
+        pd = C.POINTER(C.c_double)
+        check(lib.dspb200_eq_plan_chunk_system(self._h, C.byref(rows), C.byref(states), tk.ctypes.data_as(pd),
+                                               o.ctypes.data_as(pd), phi.ctypes.data_as(pd)))
+        return tk[:r], tk[r:r + n], o[:, :n], phi[:n, :n]
+
     def describe(self) -> np.ndarray:
         n = C.c_int()
         buf = np.zeros((16, 9))

@@ -134,8 +134,8 @@ int dspb200_eq_plan_destroy(dspb200_eq_plan* plan);
 /* z[c, :] = clip(cascade(x[c, :])); zero initial state per channel; one pass
  * over HBM for all sections.  In place (z == x) is allowed.  Two forms: the
  * chunked linear-recurrence scan on the FMA pipe (any dtype, any shape), and,
- * for fp32 batches wide enough to fill the GPU (about 4.7k channels; complex
- * poles; 16-byte aligned rows), the cascade as one linear system advanced 112
+ * for fp32 batches wide enough to fill the GPU (about 15k channels; at most 8
+ * sections; 16-byte aligned rows), the cascade as one linear system advanced 112
  * samples per tcgen05 GEMM tile with the state carried between tiles. */
 int dspb200_eq_run_f32(const dspb200_eq_plan* plan, const float* x, int64_t x_stride, float* z,
                        int64_t z_stride, int64_t channels, int64_t n, void* stream);
@@ -148,6 +148,14 @@ int dspb200_eq_host_f64(const dspb200_eq_plan* plan, const double* x, double* z,
 /* Which kernel a run of this shape would use: 0 = scan (FMA pipe), 1 = tensor. */
 int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, int64_t n,
                                 int64_t x_stride, int* kind);
+/* Introspection for tests (host only, no device needed): the chunk system the
+ * tensor-core form multiplies, in float64:  z = T x + O s,  s' = Phi s + K x
+ * over *rows = 96 samples with *states = 2 * sections states.  tk receives
+ * [T; K] as (rows + 16) x rows, o as rows x 16, phi as 16 x 16 (row-major, unused
+ * state rows / columns zero); any of them may be NULL.  *rows = 0 when the plan
+ * has no tensor form (no sections, or more than 8). */
+int dspb200_eq_plan_chunk_system(const dspb200_eq_plan* plan, int* rows, int* states, double* tk,
+                                 double* o, double* phi);
 /* Introspection for tests: number of sections and, per section, 9 doubles
  * (a00 a01 a10 a11 b0 b1 c0 c1 d) of the state-space form the kernel runs. */
 int dspb200_eq_plan_describe(const dspb200_eq_plan* plan, int* n_sections, double* state_space,

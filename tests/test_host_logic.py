@@ -99,6 +99,84 @@ def test_state_space_sections_reproduce_lfilter(lib):
     assert o.rel_err(y, ref) <= 1e-11
 
 
+def _tf32_trunc(v):
+    return (np.asarray(v, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _tf32_round(v):
+    return ((np.asarray(v, np.float32).view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@pytest.mark.parametrize("gains", [(6, -3, 4, -6, 3, -9), (15,) * 6, (-15,) * 6, (-12.0412, 15, -12.5, 6, 0, -3),
+                                   (0, 0, 0, 0, 0, 12)])
+def test_eq_chunk_system_reproduces_the_cascade(lib, gains):
+    """The tensor-core form of the EQ (csrc/eq_mma.cu) multiplies a chunk system built on the host in float64:
+    z = T x + O s, s' = Phi s + K x over 96 samples.  Stepping it in numpy must reproduce the reference cascade
+    (lfilter per active band, clip once, dsp_core.py:216-254); stepping it with the kernel's arithmetic (three-
+    product TF32 split of [T; K] x and of O s, fp32 state update) must stay inside the fp32 EQ bound."""
+    import dsp_audio_project_b200 as pk
+    gd = gains_dict(gains)
+    plan = pk.EqPlan.from_gains(48000, gd, np.float32)
+    T, K, O, Phi = plan.chunk_system()
+    L, S = T.shape[0], Phi.shape[0]
+    assert L == 96 and S == 2 * plan.n_sections and np.allclose(T, np.tril(T))
+    assert np.allclose(np.linalg.norm(K, axis=1), 1.0)             # balanced states
+    x = np.random.default_rng(11).uniform(-0.5, 0.5, L * 40 + 17)
+    n = x.size
+    xp = np.zeros(-(-n // L) * L)
+    xp[:n] = x
+    X = xp.reshape(-1, L)
+    ref = o.equalizer(x, 48000, gd)
+    # float64
+    s, out = np.zeros(S), []
+    for xk in X:
+        out.append(T @ xk + O @ s)
+        s = Phi @ s + K @ xk
+    assert np.max(np.abs(np.clip(np.concatenate(out)[:n], -1, 1) - ref)) <= 1e-10
+    # the kernel's arithmetic
+    M = np.vstack([T, K]).astype(np.float32)
+    Mh = _tf32_round(M)
+    Ml = _tf32_trunc(M - Mh)
+    Oh = _tf32_round(O.astype(np.float32))
+    Ol = _tf32_trunc(O.astype(np.float32) - Oh)
+    P32 = Phi.astype(np.float32)
+    s, out = np.zeros(S, np.float32), []
+    for xk in X.astype(np.float32):
+        xh = _tf32_trunc(xk)
+        xl = _tf32_trunc(xk - xh)
+        acc = Mh.astype(np.float64) @ xh + Ml.astype(np.float64) @ xh + Mh.astype(np.float64) @ xl
+        s1 = _tf32_trunc(s)
+        s2 = _tf32_trunc(s - s1)
+        s3 = _tf32_trunc(s - s1 - s2)
+        acc[:L] += Oh.astype(np.float64) @ (s1.astype(np.float64) + s2 + s3) + Ol.astype(np.float64) @ s1
+        acc = acc.astype(np.float32)
+        out.append(acc[:L])
+        s = (P32 @ s + acc[L:]).astype(np.float32)
+    assert np.max(np.abs(np.clip(np.concatenate(out)[:n], -1, 1) - ref)) <= 1e-4
+
+
+def test_eq_chunk_system_section_counts(lib):
+    import dsp_audio_project_b200 as pk
+    centres = [60.0, 250.0, 700.0, 1500.0, 3200.0, 6000.0, 9000.0, 14000.0, 18000.0]
+    gains = [5.0, -4.0, 7.5, -6.0, 3.0, -9.0, 12.0, -2.5, 4.0]
+    x = np.random.default_rng(12).uniform(-0.4, 0.4, 96 * 30)
+    for ns in range(0, 10):
+        plan = pk.EqPlan(48000, list(zip(centres[:ns], gains[:ns])), np.float32, clip=False)
+        cs = plan.chunk_system()
+        if ns == 0 or ns > 8:
+            assert cs is None                                      # no tensor form: clip-only copy / too many states
+            continue
+        T, K, O, Phi = cs
+        ref = x.copy()
+        for fc, g in zip(centres[:ns], gains[:ns]):
+            ref = o.difference_equation(ref, *o.peaking_biquad(fc, 48000, g))
+        s, out = np.zeros(2 * ns), []
+        for xk in x.reshape(-1, 96):
+            out.append(T @ xk + O @ s)
+            s = Phi @ s + K @ xk
+        assert np.max(np.abs(np.concatenate(out) - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref))), ns
+
+
 def test_bypass_and_argument_semantics(lib):
     from modules import dsp_core as dc
     x = np.arange(8, dtype=np.float32)

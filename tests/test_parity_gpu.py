@@ -372,7 +372,8 @@ def test_src_tensor_core_form_matches_oracle_and_tiled(pk, torch_cuda, L, M, mon
         assert plan.kernel_kind(channels, n_in) != "tensor" or 4 * channels >= 3 * (-(-channels // 256) * 256)
 
 
-@pytest.mark.parametrize("gains", [C1_GAINS, (15,) * 6, (3, 0, -2, 0, 0, 5), (0, 0, 0, 0, 0, 12)])
+@pytest.mark.parametrize("gains", [C1_GAINS, (15,) * 6, (3, 0, -2, 0, 0, 5), (0, 0, 0, 0, 0, 12), (-15,) * 6,
+                                   (-12.0412, 15, -12.5, 6, 0, -3)])
 def test_eq_tensor_core_form_matches_oracle_and_scan(pk, torch_cuda, gains, monkeypatch):
     """fp32 EQ on wide batches runs the cascade as one linear system, 112 samples per tcgen05 GEMM tile,
     the state carried from chunk to chunk in the registers of the thread that owns the channel
@@ -414,8 +415,7 @@ def test_eq_tensor_core_form_matches_oracle_and_scan(pk, torch_cuda, gains, monk
     z_scan = plan.run(x)
     monkeypatch.delenv("DSPB200_EQ_NO_MMA")
     assert float((z - z_scan).abs().max()) <= TOL_F32_EQ
-    # real poles (cuts below about -12.04 dB) and fp64 stay on the scan kernel
-    assert pk.EqPlan.from_gains(48000, gains_dict((-15,) * 6), np.float32).kernel_kind(18944, 3000) == "scan"
+    # fp64 stays on the scan kernel
     assert pk.EqPlan.from_gains(48000, gd, np.float64).kernel_kind(18944, 3000) == "scan"
 
 
