@@ -479,6 +479,43 @@ def test_eq_tensor_core_form_more_groups_than_sms(pk, torch_cuda, monkeypatch):
     assert float((z - z_scan).abs().max()) <= TOL_F32_EQ
 
 
+def test_eq_tensor_core_form_c3_channel_count_properties(pk, torch_cuda):
+    """C3's channel count (65536 = 512 groups on 148 SMs: the library slices the time axis) through the tensor form,
+    checked by properties that do not need the oracle at full size: impulse responses scale with the impulse,
+    arrive where the impulse was put, and equal the cascade's impulse response; the map is linear before the clip."""
+    torch = torch_cuda
+    ch, n = 65536, 96 * 300
+    gd = gains_dict(C1_GAINS)
+    sections = pk.select_sections(48000, gd)[1]
+    plan = pk.EqPlan(48000, sections, np.float32, clip=False)
+    assert plan.kernel_kind(ch, n) == "tensor"
+    # impulses: channel c gets amplitude a_c at time t_c
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    amp = torch.rand(ch, device="cuda", generator=gen) + 0.5
+    t_c = torch.randint(0, n - 4000, (ch,), device="cuda", generator=gen)
+    x = torch.zeros((ch, n), device="cuda", dtype=torch.float32)
+    x[torch.arange(ch, device="cuda"), t_c] = amp
+    z = plan.run(x)
+    h = np.zeros(4000)
+    h[0] = 1.0
+    for fc, g in sections:
+        h = o.difference_equation(h, *o.peaking_biquad(fc, 48000, g))
+    ht = torch.as_tensor(h, device="cuda", dtype=torch.float32)
+    pick = torch.randint(0, ch, (512,), device="cuda", generator=gen)
+    idx = t_c[pick][:, None] + torch.arange(4000, device="cuda")[None, :]
+    got = torch.gather(z[pick], 1, idx)
+    assert float((got - amp[pick][:, None] * ht[None, :]).abs().max()) <= 1e-5
+    before = torch.arange(n, device="cuda")[None, :] < t_c[pick][:, None]
+    assert float((z[pick] * before).abs().max()) == 0.0           # nothing before the impulse
+    # linearity on noise
+    x1 = torch.rand((ch, n), device="cuda", generator=gen) - 0.5
+    x.uniform_(-0.5, 0.5, generator=gen)
+    z1, z2 = plan.run(x1), plan.run(x)
+    x1.mul_(0.75).add_(x, alpha=-1.25)
+    z12 = plan.run(x1)
+    assert float((z12 - (0.75 * z1 - 1.25 * z2)).abs().max()) <= 2e-5
+
+
 def test_eq_tensor_core_form_long_stream(pk, torch_cuda, monkeypatch):
     """C3's time axis (2.88 M samples = 25 715 chunks) through the tensor form on two channel groups."""
     torch = torch_cuda
