@@ -19,14 +19,16 @@
 // clips once (dsp_core.py:254) and lays 128-byte runs of its channel into a swizzled staging tile that
 // leaves as TMA stores of [128 channels x 32 samples] (direct 32-byte vector stores from 32 channels per
 // instruction ran at a third of the speed; a shuffle transpose at a fifth).  A CTA walks a group of 128
-// channels through time, so no state ever leaves the SM; the form is used when there are enough
+// channels through time, so the state stays in registers; the form is used when there are enough
 // channel groups to fill the GPU (about 15k channels), narrower batches stay on the scan kernel.
+// With more groups than SMs the time axis is cut into slices, handed out by an atomic counter, so that
+// the last round is full; a later slice picks up the end state its predecessor left in global memory.
 //
 // Warp roles (one persistent CTA per SM): warps 0-3 epilogue (one TMEM lane quarter each), warp 4
 // TMA producer (the coefficient tiles once -- they stay resident in shared memory -- then x tiles
 // through a 5-deep ring), warp 5 MMA issuer, warps 6-7 converters.  Four accumulators let the MMAs run up to
 // three chunks ahead of the epilogue; the only serial link per chunk is
-// accumulator -> state update -> tcgen05.st -> six free-response MMAs of the next chunk.
+// accumulator -> state update -> tcgen05.st -> S/2 free-response MMAs of the next chunk.
 //
 // Non-finite inputs poison their whole 96-sample chunk (0 * NaN inside the GEMM), not only the
 // samples after them as the sequential reference does.
@@ -234,7 +236,11 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       // D fp32, A/B tf32, both K-major, M = 128 channels, N = 112 coefficient rows
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kTNn >> 3) << 17) | (uint32_t(kTM >> 4) << 24);
+      auto idesc_n = [](int n) -> uint32_t {
+        return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(kTM >> 4) << 24);
+      };
+      // T is lower triangular: k-block kb (inputs 32 kb ..) only reaches outputs 32 kb .. and the state rows, so its
+      // MMAs skip the first 32 kb coefficient rows (N = 112, 80, 48; accumulator columns and B rows shifted alike)
       uint32_t n_corr = 0;
       // third product of k-block `j` (deferred one step so the in-place conversion of its x tile overlaps the
       // first two products of the next k-block); after a chunk's last one, the free response of its start state
@@ -242,9 +248,10 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int sx = j % kXSlots;
         mbar_wait(&conv[sx], (j / kXSlots) & 1);
         tc_fence_after();
-        const uint64_t dxl = umma_desc_sw128(x_ptr(sx)), dth = umma_desc_sw128(tab_ptr(kb, 0));
+        const uint64_t dxl = umma_desc_sw128(x_ptr(sx)), dth = umma_desc_sw128(tab_ptr(kb, 0) + kb * kBK * 128);
+        const uint32_t idk = idesc_n(kTNn - kb * kBK);
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k) umma_tf32(d, dxl + 2 * k, dth + 2 * k, idesc, 1u);
+        for (int k = 0; k < kBK / 8; ++k) umma_tf32(d + kb * kBK, dxl + 2 * k, dth + 2 * k, idk, 1u);
         umma_commit(&empty_x[sx]);
         if (last_of_tile) {
           if (corr) {
@@ -254,7 +261,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < kS / 2; ++k)
-              umma_tf32_ts(d, tmem + kSCol + 8 * k, umma_desc_sw128(o_ptr((8 * k) / kBK)) + 2 * (((8 * k) % kBK) / 8), idesc, 1u);
+              umma_tf32_ts(d, tmem + kSCol + 8 * k, umma_desc_sw128(o_ptr((8 * k) / kBK)) + 2 * (((8 * k) % kBK) / 8), idesc_n(kRows), 1u);   // the end-state columns take no free response
           }
           umma_commit(&acc_full[b]);
         }
@@ -278,11 +285,13 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             mbar_wait(&full_x[sx], (it / kXSlots) & 1);
             tc_fence_after();
             const uint64_t dx = umma_desc_sw128(x_ptr(sx));
-            const uint64_t dth = umma_desc_sw128(tab_ptr(kb, 0)), dtl = umma_desc_sw128(tab_ptr(kb, 1));
+            const uint64_t dth = umma_desc_sw128(tab_ptr(kb, 0) + kb * kBK * 128);
+            const uint64_t dtl = umma_desc_sw128(tab_ptr(kb, 1) + kb * kBK * 128);
+            const uint32_t idk = idesc_n(kTNn - kb * kBK);
 #pragma unroll
             for (int k = 0; k < kBK / 8; ++k) {
-              umma_tf32(d, dx + 2 * k, dth + 2 * k, idesc, (kb | k) ? 1u : 0u);
-              umma_tf32(d, dx + 2 * k, dtl + 2 * k, idesc, 1u);
+              umma_tf32(d + kb * kBK, dx + 2 * k, dth + 2 * k, idk, (kb | k) ? 1u : 0u);
+              umma_tf32(d + kb * kBK, dx + 2 * k, dtl + 2 * k, idk, 1u);
             }
             umma_commit(&mid[sx]);
             if (have_prev) finish(it - 1, prev_kb, prev_d, prev_last, prev_b, prev_corr);
@@ -603,10 +612,7 @@ int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp) {
   for (float v : mp.phi) if (!std::isfinite(v)) return DSPB200_OK;
   DSP_CUDA(cudaMalloc(reinterpret_cast<void**>(&mp.d_table), tab.size() * sizeof(float)));
   DSP_CUDA(cudaMemcpy(mp.d_table, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
-  mp.period = 1;
   mp.kpad = kpad;
-  mp.kvalid = kRows;
-  mp.adv = kRows;
   mp.states = ks;
   mp.ok = 1;
   return DSPB200_OK;
@@ -621,7 +627,7 @@ bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const floa
                     int64_t n_in) {
   if (!mp.ok || reinterpret_cast<uintptr_t>(x) % 16 != 0 || xs % 4 != 0 || n_in < kRows) return false;
   if (reinterpret_cast<uintptr_t>(z) % 16 != 0 || zs % 4 != 0) return false;
-  if (mp.period != 1 || mp.kpad != kNkb * kBK) return false;
+  if (mp.kpad != kNkb * kBK) return false;
   if (kSmemBytes + 2048 > static_cast<size_t>(max_smem_optin())) return false;
   if (getenv("DSPB200_EQ_FORCE_MMA") != nullptr) return true;
   // a CTA walks a group of 128 channels through time: the form pays once the groups fill at least 80 % of the

@@ -40,11 +40,8 @@ constexpr int kLtiMaxStates = 16;
 struct Section;
 struct LtiMmaPlan {
   int ok = 0;
-  int period = 0;          // distinct tile phases
-  int kpad = 0;            // GEMM depth per tile in the table (multiple of 32)
-  int kvalid = 0;          // GEMM depth actually multiplied (multiple of 8)
-  int states = 0;          // padded to a multiple of 4
-  long long adv = 0;       // input samples per `period` chunks
+  int kpad = 0;            // GEMM depth per chunk in the table (= samples per chunk)
+  int states = 0;          // 2 * sections, padded to a multiple of 4
   float* d_table = nullptr;   // [hi, lo, free response][112][kpad]: rows 0..95 outputs, 96.. end states
   float phi[kLtiMaxStates * kLtiMaxStates] = {};   // state transition over one chunk
 };
