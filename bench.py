@@ -5,7 +5,7 @@
                     [--workload chain|src|eq|fft] [--clips C] [--dtype f32|f64]
 
 Default workload ("chain") is one wave of BASELINE.json's config C5 shaped like
-config C2: `--clips` (default 18944 = 148 SMs x 128 channels, 124 GB of device
+config C2: `--clips` (default 18944 = 148 SMs x 128 channels, 88 GB of device
 buffers) synthetic clips of 10 s @ 44.1 kHz per GPU, SRC 160/147 -> six-band EQ
 -> non-overlapping 4096-point Hann magnitude spectra, float32.  A "step" is one
 pass of that chain over the wave.  The metric is Msamples/s = input samples
@@ -282,9 +282,10 @@ def run_b200(args):
     gen = torch.Generator(device=dev).manual_seed(4 + rank)
     x = (torch.rand((clips, CLIP_SAMPLES), generator=gen, device=dev, dtype=t_dt) - 0.5)
 
-    # persistent device buffers so every step reuses the same memory
+    # persistent device buffers so every step reuses the same memory; as in dspb200_chain_run the EQ runs in place
+    # on the SRC output (config C5 keeps z and the spectra, y is never materialised on its own)
     y = torch.empty((clips, n_out), dtype=t_dt, device=dev)
-    z = torch.empty((clips, n_out), dtype=t_dt, device=dev)
+    z = y
     mag = torch.empty((clips, n_frames, bins), dtype=t_dt, device=dev)
 
     def step_chain():
