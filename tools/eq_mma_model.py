@@ -1,5 +1,5 @@
 """Numerical model of the tensor-core EQ (csrc/eq_mma.cu): the six-section cascade as one
-12-state linear system, advanced 112 samples at a time,
+12-state linear system, advanced 96 samples at a time,
     y_k = T x_k + O s_k ,   s_{k+1} = Phi s_k + K x_k ,
 with [T; K] x_k evaluated as the three-product TF32 split the tcgen05 kernel uses.
 Run on the CPU to see the error of the formulation against float64 lfilter before
@@ -12,7 +12,7 @@ from scipy.signal import lfilter
 sys.path.insert(0, ".")
 from oracle import dsp_oracle as o  # noqa: E402
 
-L = 112
+L = 96
 
 
 def section_ss(b, a):
