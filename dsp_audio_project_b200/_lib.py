@@ -48,6 +48,8 @@ SIGNATURES = {
     "dspb200_eq_plan_destroy": (C.c_int, [c_p]),
     "dspb200_eq_run_f32": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_eq_run_f64": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
+    "dspb200_eq_stream_chunk": (C.c_int, []),
+    "dspb200_eq_run_stream_f32": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p, C.c_int, c_p]),
     "dspb200_eq_host_f32": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64]),
     "dspb200_eq_host_f64": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64]),
     "dspb200_eq_plan_kernel_kind": (C.c_int, [c_p, c_i64, c_i64, c_i64, _pi]),

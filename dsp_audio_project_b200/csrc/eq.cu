@@ -685,7 +685,7 @@ int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs
     DSP_TRY(eq_mma_ready(plan, reinterpret_cast<const float*>(x), xs, reinterpret_cast<const float*>(z), zs, channels, n, tensor));
     if (tensor) {
       return lti_mma_run(plan->mma, reinterpret_cast<const float*>(x), xs, reinterpret_cast<float*>(z), zs,
-                         channels, n, n, plan->clip != 0, stream);
+                         channels, n, n, plan->clip != 0, nullptr, false, stream);
     }
   }
   const T* src = x;
@@ -850,6 +850,26 @@ int dspb200_eq_run_f64(const dspb200_eq_plan* plan, const double* x, int64_t xs,
                        int64_t channels, int64_t n, void* stream) {
   return eq_run<double>(plan, x, xs, z, zs, channels, n, static_cast<cudaStream_t>(stream));
 }
+int dspb200_eq_stream_chunk(void) { return lti_mma_chunk(); }
+
+int dspb200_eq_run_stream_f32(const dspb200_eq_plan* plan, const float* x, int64_t xs, float* z, int64_t zs,
+                              int64_t channels, int64_t n, float* state, int first, void* stream) {
+  DSP_CHECK(plan != nullptr && state != nullptr, "NULL argument");
+  DSP_CHECK(plan->dtype == DSPB200_F32, "the streaming form is float32 only");
+  DSP_CHECK(channels >= 0 && n >= 0, "negative shape");
+  if (channels == 0 || n == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
+  DSP_CHECK(xs >= n && zs >= n, "channel stride smaller than n");
+  DSP_TRY(ensure_device());
+  bool tensor = false;
+  DSP_TRY(eq_mma_ready(plan, nullptr, 4, nullptr, 4, 0, 0, tensor));   // builds the plan's tables
+  if (plan->mma_state != 1 || !lti_mma_possible(plan->mma, x, xs, z, zs))
+    return fail(DSPB200_ERR_UNSUPPORTED,
+                "the streaming form needs 1..8 sections and 16-byte aligned rows (x, z and both strides)");
+  return lti_mma_run(plan->mma, x, xs, z, zs, channels, n, n, plan->clip != 0, state, first == 0,
+                     static_cast<cudaStream_t>(stream));
+}
+
 int dspb200_eq_host_f32(const dspb200_eq_plan* plan, const float* x, float* z, int64_t channels, int64_t n) {
   DSP_CHECK(plan && plan->dtype == DSPB200_F32, "plan is NULL or not float32");
   return eq_host<float>(plan, x, z, channels, n);

@@ -74,6 +74,8 @@ struct LtiArgs {
   unsigned* counter;            // job dispenser
   unsigned* done;               // [n_jobs] 1 once the item's end state is in `xfer`
   float* xfer;                  // [n_jobs][kS][128] end states handed to the group's next slice
+  float* state;                 // streaming form: [channels][16] state after the block (NULL: not kept)
+  int state_in;                 // streaming form: start from `state` instead of zero
   int clip;
   unsigned long long* prof;     // development: cycles per epilogue phase (NULL = off)
   float phi[kLtiMaxStates * kLtiMaxStates];
@@ -295,7 +297,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             umma_commit(&mid[sx]);
             if (have_prev) finish(it - 1, prev_kb, prev_d, prev_last, prev_b, prev_corr);
-            have_prev = true; prev_d = d; prev_b = b; prev_kb = kb; prev_last = (kb == kNkb - 1); prev_corr = tt > 0;   // chunk 0 starts from a zero state; a later slice's first chunk from the handed-over one
+            have_prev = true; prev_d = d; prev_b = b; prev_kb = kb; prev_last = (kb == kNkb - 1); prev_corr = tt > 0 || a.state_in != 0;   // chunk 0 starts from a zero state unless one was passed in
           }
         }
       }
@@ -362,9 +364,15 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const Job jb = job_of(job);
       const int g = jb.g;
       float s[kS];
-      if (jb.h == 0) {
+      const long long chan = static_cast<long long>(g) * kTM + warp * 32 + lane;
+      if (jb.h == 0 && !a.state_in) {
 #pragma unroll
         for (int i = 0; i < kS; ++i) s[i] = 0.f;     // zero initial state per channel (lfilter, dsp_core.py:214)
+      } else if (jb.h == 0) {
+        // streaming form: the state the previous block of these channels ended in
+#pragma unroll
+        for (int i = 0; i < kS; ++i) s[i] = chan < a.channels ? __ldcg(a.state + chan * kLtiMaxStates + i) : 0.f;
+        hand_over(s);
       } else {
         // later slice of the group: its start state is the end state of the slice before, finished rounds ago
         const long long pj = job - a.n_groups;
@@ -438,6 +446,10 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           atomicAdd(a.prof + 4, static_cast<unsigned long long>(clock64() - t3));    // clip + stores
           atomicAdd(a.prof + 2, 1ull);
         }
+      }
+      if (jb.t1 == static_cast<int>(a.n_tt) && a.state != nullptr && chan < a.channels) {
+#pragma unroll
+        for (int i = 0; i < kS; ++i) a.state[chan * kLtiMaxStates + i] = s[i];
       }
       if (jb.t1 < static_cast<int>(a.n_tt)) {
         // the group goes on in a later slice: leave the end state where that slice will pick it up
@@ -623,6 +635,13 @@ void lti_mma_free(LtiMmaPlan& mp) {
   mp = LtiMmaPlan{};
 }
 
+bool lti_mma_possible(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs) {
+  return mp.ok && reinterpret_cast<uintptr_t>(x) % 16 == 0 && xs % 4 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0 &&
+         zs % 4 == 0 && mp.kpad == kNkb * kBK && kSmemBytes + 2048 <= static_cast<size_t>(max_smem_optin());
+}
+
+int lti_mma_chunk() { return kRows; }
+
 bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs, int64_t channels,
                     int64_t n_in) {
   if (!mp.ok || reinterpret_cast<uintptr_t>(x) % 16 != 0 || xs % 4 != 0 || n_in < kRows) return false;
@@ -638,7 +657,7 @@ bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const floa
 }
 
 int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int64_t zs, int64_t channels,
-                int64_t n_in, int64_t n_out, bool clip, cudaStream_t stream) {
+                int64_t n_in, int64_t n_out, bool clip, float* state, bool state_in, cudaStream_t stream) {
   CUtensorMap tm_a, tm_x, tm_z;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_x, 0, sizeof(tm_x));
@@ -657,6 +676,8 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
   DSP_CHECK(n_in < (1ll << 31) - 256 && channels < (1ll << 31) - 256 && n_out < (1ll << 31) - 256,
             "shape too large for the tensor-core EQ kernel");
   a.clip = clip ? 1 : 0;
+  a.state = state;
+  a.state_in = (state != nullptr && state_in) ? 1 : 0;
   memcpy(a.phi, mp.phi, sizeof(a.phi));
   const int64_t sms = sm_count();
   // time slices per group: with at least one group per SM a slice's predecessor ran a whole round earlier, so its end

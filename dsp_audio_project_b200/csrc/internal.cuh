@@ -58,8 +58,12 @@ int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp);
 void lti_mma_free(LtiMmaPlan& mp);
 bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs, int64_t channels,
                     int64_t n_in);
+// state (optional): [channels][16] floats in the plan's scaled basis, written with the state after the block;
+// state_in: start from it instead of zero (streaming form)
 int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int64_t zs, int64_t channels,
-                int64_t n_in, int64_t n_out, bool clip, cudaStream_t stream);
+                int64_t n_in, int64_t n_out, bool clip, float* state, bool state_in, cudaStream_t stream);
+bool lti_mma_possible(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs);
+int lti_mma_chunk();
 int fft_plan_info(const dspb200_fft_plan* plan, int* n_fft, int* dtype);
 int eq_plan_dtype(const dspb200_eq_plan* plan);
 }  // namespace dspb200

@@ -136,6 +136,35 @@ class SrcPlan:
                      _stream_ptr(x)))
         return out
 
+    def run_stream(self, x, state=None, out=None):
+        """One time block of a longer signal (float32): `state` is None for the first block, afterwards the
+        tensor this call returned for the previous block.  Blocks other than the last must be multiples of
+        `stream_chunk()` samples.  Returns (z, state)."""
+        torch = _torch()
+        _check_tensor(x, self.dtype_id, "x")
+        if self.dtype_id != F32:
+            raise ValueError("the streaming form is float32 only")
+        if out is None:
+            out = torch.empty_like(x)
+        _check_tensor(out, self.dtype_id, "out")
+        if out.shape != x.shape:
+            raise ValueError("out must have x's shape")
+        ch, n = x.shape
+        first = state is None
+        if first:
+            state = torch.zeros((ch, 16), dtype=torch.float32, device=x.device)
+        elif state.shape != (ch, 16) or state.dtype != torch.float32 or not state.is_contiguous() or state.device != x.device:
+            raise ValueError("state must be the [channels, 16] float32 tensor a previous run_stream returned")
+        with torch.cuda.device(x.device):
+            check(_lib.load().dspb200_eq_run_stream_f32(self._h, x.data_ptr(), _row_stride(x), out.data_ptr(),
+                                                        _row_stride(out), ch, n, state.data_ptr(), int(first),
+                                                        _stream_ptr(x)))
+        return out, state
+
+    @staticmethod
+    def stream_chunk() -> int:
+        return int(_lib.load().dspb200_eq_stream_chunk())
+
     def run_host(self, x):
         a = _as_host(x, self.dtype_id)
         ch, n_in = a.shape
@@ -240,6 +269,35 @@ class EqPlan:
         with torch.cuda.device(x.device):
             check(fn(self._h, x.data_ptr(), _row_stride(x), out.data_ptr(), _row_stride(out), ch, n, _stream_ptr(x)))
         return out
+
+    def run_stream(self, x, state=None, out=None):
+        """One time block of a longer signal (float32): `state` is None for the first block, afterwards the
+        tensor this call returned for the previous block.  Blocks other than the last must be multiples of
+        `stream_chunk()` samples.  Returns (z, state)."""
+        torch = _torch()
+        _check_tensor(x, self.dtype_id, "x")
+        if self.dtype_id != F32:
+            raise ValueError("the streaming form is float32 only")
+        if out is None:
+            out = torch.empty_like(x)
+        _check_tensor(out, self.dtype_id, "out")
+        if out.shape != x.shape:
+            raise ValueError("out must have x's shape")
+        ch, n = x.shape
+        first = state is None
+        if first:
+            state = torch.zeros((ch, 16), dtype=torch.float32, device=x.device)
+        elif state.shape != (ch, 16) or state.dtype != torch.float32 or not state.is_contiguous() or state.device != x.device:
+            raise ValueError("state must be the [channels, 16] float32 tensor a previous run_stream returned")
+        with torch.cuda.device(x.device):
+            check(_lib.load().dspb200_eq_run_stream_f32(self._h, x.data_ptr(), _row_stride(x), out.data_ptr(),
+                                                        _row_stride(out), ch, n, state.data_ptr(), int(first),
+                                                        _stream_ptr(x)))
+        return out, state
+
+    @staticmethod
+    def stream_chunk() -> int:
+        return int(_lib.load().dspb200_eq_stream_chunk())
 
     def run_host(self, x):
         a = _as_host(x, self.dtype_id)

@@ -141,6 +141,20 @@ int dspb200_eq_run_f32(const dspb200_eq_plan* plan, const float* x, int64_t x_st
                        int64_t z_stride, int64_t channels, int64_t n, void* stream);
 int dspb200_eq_run_f64(const dspb200_eq_plan* plan, const double* x, int64_t x_stride, double* z,
                        int64_t z_stride, int64_t channels, int64_t n, void* stream);
+/* Streaming form (float32, tensor-core kernel): the cascade over consecutive
+ * time blocks of the same channels, e.g. config C3's 65536 x 2.88 M samples in
+ * blocks that fit in HBM.  state: [channels][16] floats, opaque (the plan's
+ * internal basis), receives the state after the block; first != 0 starts from
+ * zero (dsp_core.py:214), first == 0 from `state` as the previous block left
+ * it.  Every block but the last must be a multiple of
+ * dspb200_eq_stream_chunk() samples; the blocks then reproduce one pass over
+ * the whole signal bit for bit.  The clip (:254) is applied per block, which
+ * is the same thing.  DSPB200_ERR_UNSUPPORTED for plans without a tensor form
+ * (no sections, more than 8) or rows that are not 16-byte aligned. */
+int dspb200_eq_stream_chunk(void);
+int dspb200_eq_run_stream_f32(const dspb200_eq_plan* plan, const float* x, int64_t x_stride, float* z,
+                              int64_t z_stride, int64_t channels, int64_t n, float* state, int first,
+                              void* stream);
 int dspb200_eq_host_f32(const dspb200_eq_plan* plan, const float* x, float* z, int64_t channels,
                         int64_t n);
 int dspb200_eq_host_f64(const dspb200_eq_plan* plan, const double* x, double* z, int64_t channels,

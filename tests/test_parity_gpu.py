@@ -516,6 +516,44 @@ def test_eq_tensor_core_form_c3_channel_count_properties(pk, torch_cuda):
     assert float((z12 - (0.75 * z1 - 1.25 * z2)).abs().max()) <= 2e-5
 
 
+def test_eq_streaming_blocks_reproduce_one_pass(pk, torch_cuda, monkeypatch):
+    """dspb200_eq_run_stream_f32: consecutive time blocks with the state carried between the calls (how C3's
+    65536 x 2.88 M samples fit through HBM) give the same samples as one pass, bit for bit, and match the oracle."""
+    torch = torch_cuda
+    gd = gains_dict((15, -3, 4, -14, 3, -9))
+    plan = pk.EqPlan.from_gains(48000, gd, np.float32)
+    chunk = plan.stream_chunk()
+    assert chunk == 96
+    rng = np.random.default_rng(21)
+    channels, n = 300, chunk * 50 + 36          # rows must stay 16-byte aligned for the streaming form
+    x = rng.uniform(-0.3, 0.3, (channels, n)).astype(np.float32)
+    xt = torch.as_tensor(x, device="cuda")
+    monkeypatch.setenv("DSPB200_EQ_FORCE_MMA", "1")
+    whole = plan.run(xt)
+    monkeypatch.delenv("DSPB200_EQ_FORCE_MMA")
+    cuts = [0, chunk * 7, chunk * 27, chunk * 28, n]
+    state, parts = None, []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        blk = xt[:, a:b].contiguous()
+        z, state = plan.run_stream(blk, state)
+        parts.append(z)
+    got = torch.cat(parts, dim=1)
+    assert torch.equal(got, whole)
+    pick = [0, 150, 299]
+    ref = np.stack([o.equalizer(x[c].astype(np.float64), 48000, gd) for c in pick])
+    assert o.full_scale_err(got.cpu().numpy()[pick], ref) <= TOL_F32_EQ
+    # in place on a view of a larger buffer, and the error paths
+    buf = xt.clone()
+    state = None
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        _, state = plan.run_stream(buf[:, a:b], state, out=buf[:, a:b])
+    assert torch.equal(buf, whole)
+    with pytest.raises(ValueError):
+        plan.run_stream(xt, torch.zeros((channels, 8), device="cuda"))
+    with pytest.raises(Exception):
+        pk.EqPlan(48000, [(1000.0 + 100 * i, 3.0) for i in range(9)], np.float32).run_stream(xt)
+
+
 def test_eq_tensor_core_form_long_stream(pk, torch_cuda, monkeypatch):
     """C3's time axis (2.88 M samples = 25 715 chunks) through the tensor form on two channel groups."""
     torch = torch_cuda

@@ -80,6 +80,28 @@ def main():
                 x.uniform_(-0.25, 0.25, generator=gen)
             del x
             torch.cuda.empty_cache()
+        # C3 in full: 65536 channels x 2.88 M samples as 12 blocks of 240000 with the state carried between the calls
+        # (dspb200_eq_run_stream_f32; each block is regenerated in place, 1.51 TB of traffic in all)
+        ch, n, blocks = 65536, 240_000, 12
+        x = torch.empty((ch, n), device=dev, dtype=torch.float32)
+        eq = pkg.EqPlan.from_gains(48000, GAINS, np.float32)
+        x.uniform_(-0.25, 0.25, generator=gen)
+        _, st = eq.run_stream(x, None, out=x)                   # warm-up
+        torch.cuda.synchronize()
+        total = 0.0
+        st = None
+        for b in range(blocks):
+            x.uniform_(-0.25, 0.25, generator=gen)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, st = eq.run_stream(x, st, out=x)
+            e1.record()
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
+        report(f"C3 full EQ {ch}x{n * blocks} as {blocks} streamed blocks, C1 gains f32 (kernel time only)", total,
+               ch * n * blocks, 8 * ch * n * blocks, {"kernel": "tensor", "ms_per_block": round(total / blocks, 3)})
+        del x
+        torch.cuda.empty_cache()
         if args.only == "c3t":
             return
     for tdt, ndt, es, tag in ((torch.float32, np.float32, 4, "f32"), (torch.float64, np.float64, 8, "f64")):
