@@ -26,7 +26,7 @@
 //
 // Warp roles (one persistent CTA per SM): warps 0-3 epilogue (one TMEM lane quarter each), warp 4
 // TMA producer (the coefficient tiles once -- they stay resident in shared memory -- then x tiles
-// through a 5-deep ring), warp 5 MMA issuer, warps 6-7 converters.  Four accumulators let the MMAs run up to
+// through a 6-deep ring), warp 5 MMA issuer, warps 6-7 converters.  Four accumulators let the MMAs run up to
 // three chunks ahead of the epilogue; the only serial link per chunk is
 // accumulator -> state update -> tcgen05.st -> S/2 free-response MMAs of the next chunk.
 //
@@ -50,7 +50,7 @@ constexpr int kRows = 96;       // samples per chunk (three 32-sample k-blocks, 
 constexpr int kTNn = kRows + kLtiMaxStates;   // 112 coefficient rows (MMA N): outputs + end states
 constexpr int kBK = 32;         // k-values per stage (one 128-byte swizzle row)
 constexpr int kNkb = kRows / kBK;
-constexpr int kXSlots = 5;
+constexpr int kXSlots = 6;
 constexpr int kStages = 2;       // staging tiles of the TMA stores
 constexpr int kJobQ = 16;        // job queue depth; no role runs more than ~7 items ahead of the epilogue
 constexpr int kAccs = 4;
@@ -59,10 +59,19 @@ constexpr int kEpiWarps = 4;
 constexpr int kConvWarps = 2;      // 8 warps in all: registers are allotted in groups of four warps, 10 warps would cap the kernel at 168
 constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kConvWarp0 = kEpiWarps + 2;
 constexpr int kThreads = (kConvWarp0 + kConvWarps) * 32;
-constexpr uint32_t kTabBytes = kTNn * kBK * 4;   // 14 KB: one k-block of [T; K] (hi or lo) or of O
 constexpr uint32_t kXBytes = kTM * kBK * 4;      // 16 KB: one k-block of x
-constexpr int kTabTiles = 2 * kNkb + 2;          // [T; K] hi/lo per k-block, then two k-blocks of the free-response operand
-constexpr size_t kSmemBytes = static_cast<size_t>(kTabTiles) * kTabBytes + (kXSlots + kStages) * kXBytes + 1024;
+// resident coefficient tiles, 128 bytes (32 k-values) per row.  T is lower triangular: the tile of k-block kb only
+// holds rows 32 kb .. 111 (112, 80, 48 rows), hi and lo; then two k-blocks of the free-response operand, 96 rows each
+constexpr uint32_t tab_rows(int kb) { return kTNn - kb * kBK; }
+constexpr uint32_t tab_off(int kb, int hl) {
+  uint32_t off = 0;
+  for (int j = 0; j < kb; ++j) off += 2 * tab_rows(j) * 128;
+  return off + hl * tab_rows(kb) * 128;
+}
+constexpr uint32_t kOOff = tab_off(kNkb, 0);
+constexpr uint32_t kOBytes = kRows * 128;
+constexpr uint32_t kTabTotal = kOOff + 2 * kOBytes;   // 84 KB
+constexpr size_t kSmemBytes = static_cast<size_t>(kTabTotal) + (kXSlots + kStages) * kXBytes + 1024;
 
 struct LtiArgs {
   float* z; long long z_stride;
@@ -187,11 +196,11 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  unsigned char* xring = smem + static_cast<size_t>(kTabTiles) * kTabBytes;
+  unsigned char* xring = smem + kTabTotal;
   auto x_ptr = [&](int s) -> unsigned char* { return xring + static_cast<size_t>(s) * kXBytes; };
   unsigned char* stage0 = x_ptr(kXSlots);                                         // kStages x [128 channels][32 samples], swizzled
-  auto tab_ptr = [&](int kb, int hl) -> unsigned char* { return smem + static_cast<size_t>(kb * 2 + hl) * kTabBytes; };
-  auto o_ptr = [&](int kb) -> unsigned char* { return smem + static_cast<size_t>(2 * kNkb + kb) * kTabBytes; };
+  auto tab_ptr = [&](int kb, int hl) -> unsigned char* { return smem + tab_off(kb, hl); };   // first row held: 32 kb
+  auto o_ptr = [&](int kb) -> unsigned char* { return smem + kOOff + kb * kOBytes; };
   // the i-th work item of this CTA (-1: none left); group, slice and chunk range of an item
   auto next_job = [&](uint32_t i) -> long long {
     mbar_wait(&job_full[i % kJobQ], (i / kJobQ) & 1);
@@ -213,10 +222,13 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       tma_prefetch_desc(&tm_a);
       tma_prefetch_desc(&tm_x);
-      mbar_expect_tx(tab_full, kTabTiles * kTabBytes);
+      mbar_expect_tx(tab_full, kTabTotal);
       for (int kb = 0; kb < kNkb; ++kb)
-        for (int hl = 0; hl < 2; ++hl) tma_load_2d(tab_ptr(kb, hl), &tm_a, kb * kBK, hl * kTNn, tab_full);
-      for (int kb = 0; kb < 2; ++kb) tma_load_2d(o_ptr(kb), &tm_a, kb * kBK, 2 * kTNn, tab_full);
+        for (int hl = 0; hl < 2; ++hl)
+          for (int r = kb * kBK; r < kTNn; r += 16)         // boxes of 16 rows
+            tma_load_2d(tab_ptr(kb, hl) + (r - kb * kBK) * 128, &tm_a, kb * kBK, hl * kTNn + r, tab_full);
+      for (int kb = 0; kb < 2; ++kb)
+        for (int r = 0; r < kRows; r += 16) tma_load_2d(o_ptr(kb) + r * 128, &tm_a, kb * kBK, 2 * kTNn + r, tab_full);
       uint32_t it = 0;
       for (uint32_t ji = 0;; ++ji) {
         long long j = static_cast<long long>(atomicAdd(a.counter, 1u));
@@ -250,7 +262,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int sx = j % kXSlots;
         mbar_wait(&conv[sx], (j / kXSlots) & 1);
         tc_fence_after();
-        const uint64_t dxl = umma_desc_sw128(x_ptr(sx)), dth = umma_desc_sw128(tab_ptr(kb, 0) + kb * kBK * 128);
+        const uint64_t dxl = umma_desc_sw128(x_ptr(sx)), dth = umma_desc_sw128(tab_ptr(kb, 0));
         const uint32_t idk = idesc_n(kTNn - kb * kBK);
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) umma_tf32(d + kb * kBK, dxl + 2 * k, dth + 2 * k, idk, 1u);
@@ -287,8 +299,8 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             mbar_wait(&full_x[sx], (it / kXSlots) & 1);
             tc_fence_after();
             const uint64_t dx = umma_desc_sw128(x_ptr(sx));
-            const uint64_t dth = umma_desc_sw128(tab_ptr(kb, 0) + kb * kBK * 128);
-            const uint64_t dtl = umma_desc_sw128(tab_ptr(kb, 1) + kb * kBK * 128);
+            const uint64_t dth = umma_desc_sw128(tab_ptr(kb, 0));
+            const uint64_t dtl = umma_desc_sw128(tab_ptr(kb, 1));
             const uint32_t idk = idesc_n(kTNn - kb * kBK);
 #pragma unroll
             for (int k = 0; k < kBK / 8; ++k) {
@@ -664,7 +676,7 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
   memset(&tm_z, 0, sizeof(tm_z));
   DSP_TRY(encode_tmap_2d(&tm_a, DSPB200_F32, mp.d_table, static_cast<uint64_t>(mp.kpad),
                          static_cast<uint64_t>(3) * kTNn, static_cast<uint64_t>(mp.kpad) * sizeof(float),
-                         kBK, kTNn, true));
+                         kBK, 16, true));
   DSP_TRY(encode_tmap_2d(&tm_x, DSPB200_F32, x, static_cast<uint64_t>(n_in), static_cast<uint64_t>(channels),
                          static_cast<uint64_t>(xs) * sizeof(float), kBK, kTM, true));
   DSP_TRY(encode_tmap_2d(&tm_z, DSPB200_F32, z, static_cast<uint64_t>(n_out), static_cast<uint64_t>(channels),
