@@ -26,7 +26,7 @@
 //
 // Warp roles (one persistent CTA per SM): warps 0-3 epilogue (one TMEM lane quarter each), warp 4
 // TMA producer (the coefficient tiles once -- they stay resident in shared memory -- then x tiles
-// through a 6-deep ring), warp 5 MMA issuer, warps 6-7 converters.  Four accumulators let the MMAs run up to
+// through a 7-deep ring), warp 5 MMA issuer, warps 6-7 converters.  Four accumulators let the MMAs run up to
 // three chunks ahead of the epilogue; the only serial link per chunk is
 // accumulator -> state update -> tcgen05.st -> S/2 free-response MMAs of the next chunk.
 //
@@ -50,8 +50,8 @@ constexpr int kRows = 96;       // samples per chunk (three 32-sample k-blocks, 
 constexpr int kTNn = kRows + kLtiMaxStates;   // 112 coefficient rows (MMA N): outputs + end states
 constexpr int kBK = 32;         // k-values per stage (one 128-byte swizzle row)
 constexpr int kNkb = kRows / kBK;
-constexpr int kXSlots = 6;
-constexpr int kStages = 2;       // staging tiles of the TMA stores
+constexpr int kXSlots = 7;
+constexpr int kStages = 1;       // staging tiles of the TMA stores
 constexpr int kJobQ = 16;        // job queue depth; no role runs more than ~7 items ahead of the epilogue
 constexpr int kAccs = 4;
 constexpr int kSCol = kAccs * kTNn;           // TMEM columns 448..511: the split start states (A operand of the correction)
