@@ -63,6 +63,8 @@ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 // the library does not link libcuda).
 int encode_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t dim0, uint64_t dim1,
                    uint64_t stride1_bytes, uint32_t box0, uint32_t box1, bool swizzle128 = false);
+int encode_tmap_2d_sw(CUtensorMap* map, int dtype, const void* base, uint64_t dim0, uint64_t dim1,
+                      uint64_t stride1_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes);   // 0, 64 or 128
 
 #ifdef __CUDACC__
 // ---- device utilities ----------------------------------------------------

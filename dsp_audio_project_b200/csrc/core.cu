@@ -81,6 +81,11 @@ int max_smem_optin() {
 
 int encode_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t dim0, uint64_t dim1,
                    uint64_t stride1_bytes, uint32_t box0, uint32_t box1, bool swizzle128) {
+  return encode_tmap_2d_sw(map, dtype, base, dim0, dim1, stride1_bytes, box0, box1, swizzle128 ? 128 : 0);
+}
+
+int encode_tmap_2d_sw(CUtensorMap* map, int dtype, const void* base, uint64_t dim0, uint64_t dim1,
+                      uint64_t stride1_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -103,7 +108,7 @@ int encode_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t dim0,
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dtype == DSPB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(DSPB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
