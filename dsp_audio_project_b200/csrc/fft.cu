@@ -81,6 +81,13 @@ __device__ __forceinline__ float2 pmul(float2 a, float2 b) {   // elementwise (a
 __device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
 __device__ __forceinline__ float2 pscale(float2 a, float s) { return fmul2s(a, s); }
 __device__ __forceinline__ double2 pscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {     // elementwise a*b + c
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ double2 fma2(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
 template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
 template <typename C> __device__ __forceinline__ C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
 // magnitude (or its dB value) from |X|^2
@@ -142,6 +149,10 @@ template <typename T> struct FftArgs {
   long long x_stride;
   long long n_valid, offset, hop, n_frames;
   const T* window;         // Hann [2*nc] or nullptr
+  // Hann by angle addition (fixed-size kernel): per-thread (-cos/2, sin/2) of samples 2t, 2t+1 and the
+  // step rotations cos/sin(u * 2 pi 2Q/(N-1)), duplicated into both halves of a packed operand
+  const T* hann_ab;        // [Q][4] = (-cos(phi_2t)/2, -cos(phi_2t+1)/2, sin(phi_2t)/2, sin(phi_2t+1)/2)
+  C hann_cc[16], hann_ss[16];
   int db;                  // write 20*log10(mag + 1e-12) instead of mag (app.py:207-210)
   // geometry
   int nc;                  // complex points of the whole transform
@@ -153,6 +164,9 @@ template <typename T> struct FftArgs {
   int tw_offset[8];
   int tw_total;
   int tw_in_smem;
+  const C* tw_tree;        // radix-16 passes only: [ns_p][kTreePitch] = W^k, W^2k, W^4k, W^8k (product-tree form)
+  int tw_tree_offset[8];
+  int tw_tree_total;
   const C* tw_top;         // W_nc[k]
   const C* tw_post;        // W_(2nc)[k], k = 0..nc/2
   // output
@@ -175,6 +189,7 @@ __device__ __forceinline__ void gather_butterflies(typename Cpx<T>::type* v, con
 }
 
 constexpr int kTwPitch = 17;   // per-pass twiddle rows [k][17]: 16-lane 8-byte reads hit distinct banks
+constexpr int kTreePitch = 5;  // compact rows [k][5]: (10 k + 2 c) mod 32 is distinct over 16 consecutive k
 
 template <typename T, int R>
 __device__ __forceinline__ void compute_store_pass(const typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
@@ -335,7 +350,11 @@ template <> struct CtPlan<2048> { static constexpr int NP = 3; static constexpr 
 template <> struct CtPlan<4096> { static constexpr int NP = 3; static constexpr int R[4] = {16, 16, 16, 1}; };
 template <> struct CtPlan<8192> { static constexpr int NP = 4; static constexpr int R[4] = {2, 16, 16, 16}; };
 
-template <typename T, int M, int R, int NS>
+// VAR bit 0: radix-16 twiddles W^r, r = 1..15, from W^1, W^2, W^4, W^8 by a product tree (<= 3
+//            roundings deep) instead of 15 shared-memory reads; bit 1: Hann by angle addition instead
+//            of a table read per sample; bit 2: the last pass stores without padding (its stores and
+//            the epilogue's mirrored reads are unit-stride, the pad only costs them a 2-way conflict).
+template <typename T, int M, int R, int NS, int VAR>
 __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
                                         const typename Cpx<T>::type* __restrict__ tw, const int t) {
   typedef typename Cpx<T>::type C;
@@ -347,7 +366,18 @@ __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typena
     const int j = t + b * Q;
     const int k = j & (NS - 1);
     C* w = v + b * R;
-    if constexpr (NS > 1) {
+    if constexpr (NS > 1 && R == 16 && (VAR & 1) != 0 && sizeof(T) == 4) {
+      const C* row = tw + k * kTreePitch;
+      const C w1 = row[0], w2 = row[1], w4 = row[2], w8 = row[3];
+      const C w3 = cmul(w1, w2);
+      w[1] = cmul(w[1], w1); w[2] = cmul(w[2], w2); w[3] = cmul(w[3], w3); w[4] = cmul(w[4], w4);
+      const C w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+      w[5] = cmul(w[5], w5); w[6] = cmul(w[6], w6); w[7] = cmul(w[7], w7); w[8] = cmul(w[8], w8);
+      w[9] = cmul(w[9], cmul(w1, w8)); w[10] = cmul(w[10], cmul(w2, w8));
+      w[11] = cmul(w[11], cmul(w3, w8)); w[12] = cmul(w[12], cmul(w4, w8));
+      w[13] = cmul(w[13], cmul(w5, w8)); w[14] = cmul(w[14], cmul(w6, w8));
+      w[15] = cmul(w[15], cmul(w7, w8));
+    } else if constexpr (NS > 1) {
       const C* row = tw + k * kTwPitch;
       C wv[R];
 #pragma unroll
@@ -357,13 +387,19 @@ __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typena
     }
     Dft<T, R>::run(w);
     const int base = (j - k) * R + k;
-    C* sp = s + base + (base >> kPadShift);           // padded(base + r*NS) = this + static offset
+    if constexpr ((VAR & 4) != 0 && NS * R == M && B == 1) {
+      C* sp = s + base;                                 // last pass: base == t, unit stride across the warp
 #pragma unroll
-    for (int r = 0; r < R; ++r) sp[r * NS + ((r * NS) >> kPadShift)] = w[r];
+      for (int r = 0; r < R; ++r) sp[r * NS] = w[r];
+    } else {
+      C* sp = s + base + (base >> kPadShift);           // padded(base + r*NS) = this + static offset
+#pragma unroll
+      for (int r = 0; r < R; ++r) sp[r * NS + ((r * NS) >> kPadShift)] = w[r];
+    }
   }
 }
 
-template <typename T, int M, int P, int NS>
+template <typename T, int M, int P, int NS, int VAR = 0>
 __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
                                           const typename Cpx<T>::type* tw, const int* tw_offset, const int t) {
   typedef typename Cpx<T>::type C;
@@ -381,15 +417,16 @@ __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename C
       }
       __syncthreads();
     }
-    ct_pass<T, M, R, NS>(tmp, s, tw + tw_offset[P], t);
+    ct_pass<T, M, R, NS, VAR>(tmp, s, tw + tw_offset[P], t);   // tw_offset: the table's own offsets (full or tree)
     __syncthreads();
-    ct_passes<T, M, P + 1, NS * R>(tmp, s, tw, tw_offset, t);
+    ct_passes<T, M, P + 1, NS * R, VAR>(tmp, s, tw, tw_offset, t);
   }
 }
 
-template <typename T, int M> struct CtBounds {
+template <typename T, int M, int VAR = 0> struct CtBounds {
   static constexpr int Q = M / 16;
-  static constexpr int kMinBlocks = sizeof(T) == 4 ? (640 / Q > 0 ? (640 / Q > 16 ? 16 : 640 / Q) : 1)
+  static constexpr int kThreads = (VAR & 16) ? 896 : ((VAR & 8) ? 768 : 640);   // resident threads per SM aimed at
+  static constexpr int kMinBlocks = sizeof(T) == 4 ? (kThreads / Q > 0 ? (kThreads / Q > 16 ? 16 : kThreads / Q) : 1)
                                                    : (256 / Q > 0 ? (256 / Q > 8 ? 8 : 256 / Q) : 1);
 };
 
@@ -400,26 +437,32 @@ template <> __device__ __forceinline__ float mag_sqrt<float>(float v) {   // MUF
   return r;
 }
 
-template <typename T, int MODE, int M, bool kTwSmem>
-__global__ void __launch_bounds__(M / 16, (CtBounds<T, M>::kMinBlocks))
+template <typename T, int MODE, int M, bool kTwSmem, int VAR = 0>
+__global__ void __launch_bounds__(M / 16, (CtBounds<T, M, VAR>::kMinBlocks))
 fft_fixed_kernel(const FftArgs<T> a) {
   typedef typename Cpx<T>::type C;
   constexpr int Q = M / 16;
   constexpr bool kReal = (MODE == 0 || MODE == 1);
   constexpr bool kSplit = (MODE == 1 || MODE == 3);   // part of a top-level radix split (r_top > 1)
+  constexpr bool kHannFly = (VAR & 2) != 0 && MODE == 0 && sizeof(T) == 4;
+  constexpr bool kFlatLast = (VAR & 4) != 0 && CtPlan<M>::R[CtPlan<M>::NP - 1] == 16;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* s = reinterpret_cast<C*>(smem_raw);
   const int t = threadIdx.x;
   C* stw = s + padded(M) + 1;
+  constexpr bool kTree = (VAR & 1) != 0 && sizeof(T) == 4;
+  const C* tw_src = kTree ? a.tw_tree : a.tw_pass;
+  const int tw_count = kTree ? a.tw_tree_total : a.tw_total;
+  const int* tw_offset = kTree ? a.tw_tree_offset : a.tw_offset;
   if constexpr (kTwSmem) {
-    for (int i = t; i < a.tw_total; i += Q) stw[i] = a.tw_pass[i];
+    for (int i = t; i < tw_count; i += Q) stw[i] = tw_src[i];
     __syncthreads();
   }
-  const C* tw = kTwSmem ? stw : a.tw_pass;
+  const C* tw = kTwSmem ? stw : tw_src;
   // MODE 0 keeps the real-split twiddles W_2M^k, k <= M/2, in shared memory as well
   const C* twp = a.tw_post;
   if constexpr (MODE == 0 && kTwSmem) {
-    C* sp = stw + a.tw_total;
+    C* sp = stw + tw_count;
     for (int i = t; i <= M / 2; i += Q) sp[i] = a.tw_post[i];
     twp = sp;
     __syncthreads();
@@ -473,6 +516,13 @@ fft_fixed_kernel(const FftArgs<T> a) {
     }
   };
 
+  C hann_a = {T(0), T(0)}, hann_b = {T(0), T(0)};
+  if constexpr (kHannFly) {
+    if (a.window) {
+      hann_a = reinterpret_cast<const C*>(a.hann_ab)[2 * t];
+      hann_b = reinterpret_cast<const C*>(a.hann_ab)[2 * t + 1];
+    }
+  }
   C tmp[16];
   if (blockIdx.x < a.n_items) fetch(blockIdx.x, tmp);
   for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -483,7 +533,14 @@ fft_fixed_kernel(const FftArgs<T> a) {
     if constexpr (kReal) {
       c = f / a.n_frames;
       fr = f - c * a.n_frames;
-      if (a.window) {
+      if constexpr (kHannFly) {
+        if (a.window) {
+          const C half = {T(0.5), T(0.5)};
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            tmp[u] = pmul(tmp[u], fma2(hann_a, a.hann_cc[u], fma2(hann_b, a.hann_ss[u], half)));
+        }
+      } else if (a.window) {
         C wv[16];
         if constexpr (!kSplit) {
           const C* wp = reinterpret_cast<const C*>(a.window) + t;
@@ -499,19 +556,19 @@ fft_fixed_kernel(const FftArgs<T> a) {
       }
     }
     __syncthreads();   // previous item's readers are done with s
-    ct_passes<T, M, 0, 1>(tmp, s, tw, a.tw_offset, t);
+    ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t);
     // the next item's loads fly while this item's epilogue reads shared memory
     if (item + gridDim.x < a.n_items) fetch(item + gridDim.x, tmp);
     if constexpr (MODE == 0) {
       T* mg = a.mag + c * a.mag_channel_stride + fr * a.mag_frame_stride;
       constexpr int NC = M;   // r_top == 1
-      const C* lp = s + t + (t >> kPadShift);
+      const C* lp = kFlatLast ? s + t : s + t + (t >> kPadShift);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {          // k = t + i*Q covers 0 .. NC/2 - 1
         const int k = t + i * Q;
-        const C A = lp[i * (Q + Q / 16)];
+        const C A = lp[kFlatLast ? i * Q : i * (Q + Q / 16)];
         const int kb = (NC - k) & (NC - 1);
-        const C Bc = cconj(s[kb + (kb >> kPadShift)]);
+        const C Bc = cconj(s[kFlatLast ? kb : kb + (kb >> kPadShift)]);
         const C xe = pscale(cadd(A, Bc), T(0.5));              // (A + conj B) / 2
         const C xo = pscale(mul_neg_i(csub(A, Bc)), T(0.5));   // -i (A - conj B) / 2
         const C tt = cmul(xo, twp[k]);
@@ -520,19 +577,19 @@ fft_fixed_kernel(const FftArgs<T> a) {
         mg[NC - k] = finish_mag(qq.x * qq.x + qq.y * qq.y, a.db);
       }
       if (t == 0) {                          // k = NC/2: both magnitudes coincide
-        const C A = s[padded(NC / 2)];
+        const C A = s[kFlatLast ? NC / 2 : padded(NC / 2)];
         mg[NC / 2] = finish_mag(A.x * A.x + A.y * A.y, a.db);
       }
     } else if constexpr (MODE == 2) {
       C* o = a.out + f * a.nc;
-      const C* lp = s + t + (t >> kPadShift);
+      const C* lp = kFlatLast ? s + t : s + t + (t >> kPadShift);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) o[t + u * Q] = lp[u * (Q + Q / 16)];
+      for (int u = 0; u < 16; ++u) o[t + u * Q] = lp[kFlatLast ? u * Q : u * (Q + Q / 16)];
     } else {
       C* o = a.out + item * M;
-      const C* lp = s + t + (t >> kPadShift);
+      const C* lp = kFlatLast ? s + t : s + t + (t >> kPadShift);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) o[t + u * Q] = lp[u * (Q + Q / 16)];
+      for (int u = 0; u < 16; ++u) o[t + u * Q] = lp[kFlatLast ? u * Q : u * (Q + Q / 16)];
     }
   }
 }
@@ -812,6 +869,9 @@ struct FftSide {
   void* d_tw_pass = nullptr;
   int tw_offset[8] = {0};
   int tw_total = 0;
+  void* d_tw_tree = nullptr;
+  int tw_tree_offset[8] = {0};
+  int tw_tree_total = 0;
   void* d_tw_top = nullptr;
   void* d_tw_post = nullptr;
 };
@@ -826,6 +886,8 @@ struct dspb200_fft_plan {
   void* d_fs_hi = nullptr;
   void* d_fs_lo = nullptr;
   void* d_window = nullptr;
+  void* d_hann_ab = nullptr;   // on-the-fly Hann of the fixed-size kernel: per-thread (-cos/2, sin/2) pairs
+  double hann_cos[16] = {0}, hann_sin[16] = {0};   // cos/sin(u * 2 pi 2Q/(N-1))
   void* d_tw_full = nullptr;   // W_N, for the direct small-size kernel
 };
 
@@ -890,6 +952,32 @@ static int build_side(FftSide& s, int nc, bool real) {
       DSP_CUDA(cudaMalloc(&s.d_tw_pass, h.size() * sizeof(C)));
       DSP_CUDA(cudaMemcpy(s.d_tw_pass, h.data(), h.size() * sizeof(C), cudaMemcpyHostToDevice));
     }
+    // compact form for the product tree: W^(k), W^(2k), W^(4k), W^(8k) of every radix-16 pass
+    std::vector<C> g;
+    ns = 1;
+    for (int p = 0; p < s.n_pass; ++p) {
+      const int R = s.radix[p];
+      s.tw_tree_offset[p] = static_cast<int>(g.size());
+      if (ns > 1 && R == 16) {
+        for (int k = 0; k < ns; ++k)
+          for (int c = 0; c < kTreePitch; ++c) {
+            C w; w.x = T(1); w.y = T(0);
+            if (c < 4) {
+              const long double ang = -2.0L * kPiL * static_cast<long double>(1 << c) * static_cast<long double>(k) /
+                                      (static_cast<long double>(ns) * static_cast<long double>(R));
+              w.x = static_cast<T>(cosl(ang));
+              w.y = static_cast<T>(sinl(ang));
+            }
+            g.push_back(w);
+          }
+      }
+      ns *= R;
+    }
+    s.tw_tree_total = static_cast<int>(g.size());
+    if (!g.empty()) {
+      DSP_CUDA(cudaMalloc(&s.d_tw_tree, g.size() * sizeof(C)));
+      DSP_CUDA(cudaMemcpy(s.d_tw_tree, g.data(), g.size() * sizeof(C), cudaMemcpyHostToDevice));
+    }
   }
   if (s.r_top > 1) DSP_TRY(upload_twiddles<T>(nc, nc, &s.d_tw_top));
   if (real) DSP_TRY(upload_twiddles<T>(2 * nc, nc / 2 + 1, &s.d_tw_post));
@@ -942,6 +1030,26 @@ static int plan_build(dspb200_fft_plan* p) {
     }
     DSP_CUDA(cudaMalloc(&p->d_window, w.size() * sizeof(T)));
     DSP_CUDA(cudaMemcpy(p->d_window, w.data(), w.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (p->real_side.r_top == 1 && p->real_side.m >= 16 && N > 1) {
+      // sample n = 2(t + uQ) + {0,1}:  w = 1/2 - cos(phi_t + u D)/2 = 1/2 + A cos(uD) + B sin(uD),
+      // A = -cos(phi_t)/2, B = sin(phi_t)/2, phi_n = 2 pi n/(N-1), D = 2 pi 2Q/(N-1)
+      const int Q = p->real_side.m / 16;
+      const long double step = 2.0L * kPiL / static_cast<long double>(N - 1);
+      std::vector<T> ab(static_cast<size_t>(Q) * 4);
+      for (int t = 0; t < Q; ++t)
+        for (int h = 0; h < 2; ++h) {
+          const long double phi = step * static_cast<long double>(2 * t + h);
+          ab[static_cast<size_t>(t) * 4 + h] = static_cast<T>(-0.5L * cosl(phi));
+          ab[static_cast<size_t>(t) * 4 + 2 + h] = static_cast<T>(0.5L * sinl(phi));
+        }
+      for (int u = 0; u < 16; ++u) {
+        const long double d = step * static_cast<long double>(2 * Q) * static_cast<long double>(u);
+        p->hann_cos[u] = static_cast<double>(cosl(d));
+        p->hann_sin[u] = static_cast<double>(sinl(d));
+      }
+      DSP_CUDA(cudaMalloc(&p->d_hann_ab, ab.size() * sizeof(T)));
+      DSP_CUDA(cudaMemcpy(p->d_hann_ab, ab.data(), ab.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
   }
   return DSPB200_OK;
 }
@@ -967,6 +1075,9 @@ static void fill_args(FftArgs<T>& a, const FftSide& s) {
   a.tw_pass = static_cast<const C*>(s.d_tw_pass);
   for (int i = 0; i < 8; ++i) a.tw_offset[i] = s.tw_offset[i];
   a.tw_total = s.tw_total;
+  a.tw_tree = static_cast<const C*>(s.d_tw_tree);
+  for (int i = 0; i < 8; ++i) a.tw_tree_offset[i] = s.tw_tree_offset[i];
+  a.tw_tree_total = s.tw_tree_total;
   a.tw_in_smem = 0;
   a.tw_top = static_cast<const C*>(s.d_tw_top);
   a.tw_post = static_cast<const C*>(s.d_tw_post);
@@ -995,15 +1106,35 @@ static int launch_stockham_t(FftArgs<T> a, cudaStream_t stream) {
 template <typename T, int MODE, int M>
 static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
   typedef typename Cpx<T>::type C;
+  int var = 0;
+  if constexpr (sizeof(T) == 4 && MODE == 0 && M == 2048) {
+    const char* ev = getenv("DSPB200_FFT_VAR");
+    var = ev ? atoi(ev) : 0;
+    if (!(var == 6 || var == 7 || var == 15 || var == 31)) var = 0;
+    if (a.window != nullptr && a.hann_ab == nullptr) var = 0;
+  }
+  const bool tree = (var & 1) != 0;
   size_t smem = static_cast<size_t>(padded(M) + 1) * sizeof(C);
-  const size_t tw_bytes = static_cast<size_t>(a.tw_total) * sizeof(C);
+  const size_t tw_bytes = static_cast<size_t>(tree ? a.tw_tree_total : a.tw_total) * sizeof(C);
   a.tw_in_smem = (tw_bytes > 0 && tw_bytes <= 24 * 1024) ? 1 : 0;
   if (a.tw_in_smem) smem += tw_bytes + (MODE == 0 ? static_cast<size_t>(M / 2 + 1) * sizeof(C) : 0);
-  auto kern = a.tw_in_smem ? fft_fixed_kernel<T, MODE, M, true> : fft_fixed_kernel<T, MODE, M, false>;
+  void (*kern)(const FftArgs<T>) = a.tw_in_smem ? fft_fixed_kernel<T, MODE, M, true> : fft_fixed_kernel<T, MODE, M, false>;
+  if constexpr (sizeof(T) == 4 && MODE == 0 && M == 2048) {
+    if (a.tw_in_smem) {
+      switch (var) {
+        case 6: kern = fft_fixed_kernel<T, MODE, M, true, 6>; break;
+        case 7: kern = fft_fixed_kernel<T, MODE, M, true, 7>; break;
+        case 15: kern = fft_fixed_kernel<T, MODE, M, true, 15>; break;
+        case 31: kern = fft_fixed_kernel<T, MODE, M, true, 31>; break;
+        default: break;
+      }
+    }
+  }
   DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 1;
   DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M / 16, smem));
   if (per_sm < 1) per_sm = 1;
+  if (getenv("DSPB200_FFT_TRACE")) fprintf(stderr, "fft_fixed M=%d var=%d smem=%zu per_sm=%d\n", M, var, smem, per_sm);
   const long long cap = static_cast<long long>(sm_count()) * per_sm;
   const int grid = static_cast<int>(a.n_items < cap ? a.n_items : cap);
   kern<<<grid, M / 16, smem, stream>>>(a);
@@ -1081,6 +1212,11 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
   FftArgs<T> a{};
   a.x = x; a.x_stride = xs; a.n_valid = n_valid; a.offset = offset; a.hop = hop; a.n_frames = n_frames;
   a.window = static_cast<const T*>(p->d_window);
+  a.hann_ab = static_cast<const T*>(p->d_hann_ab);
+  for (int u = 0; u < 16; ++u) {
+    a.hann_cc[u].x = a.hann_cc[u].y = static_cast<T>(p->hann_cos[u]);
+    a.hann_ss[u].x = a.hann_ss[u].y = static_cast<T>(p->hann_sin[u]);
+  }
   a.db = p->db;
   a.mag = mag; a.mag_frame_stride = mfs; a.mag_channel_stride = mcs;
   const FftSide& s = p->real_side;
@@ -1250,10 +1386,12 @@ int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
   FftSide* sides[4] = {&p->real_side, &p->c2c_side, &p->fs_cols, &p->fs_rows};
   for (FftSide* s : sides) {
     cudaFree(s->d_tw_pass);
+    cudaFree(s->d_tw_tree);
     cudaFree(s->d_tw_top);
     cudaFree(s->d_tw_post);
   }
   cudaFree(p->d_window);
+  cudaFree(p->d_hann_ab);
   cudaFree(p->d_tw_full);
   delete p;
   return DSPB200_OK;

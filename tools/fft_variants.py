@@ -1,0 +1,46 @@
+"""Experiment: the 4096-point Hann |FFT| kernel variants (DSPB200_FFT_VAR bit mask, see ct_pass in
+csrc/fft.cu) against the oracle on a small case and timed on C5-shaped frames.
+Usage (GPU box): python tools/fft_variants.py [clips] [variants...]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dsp_audio_project_b200 as pkg          # noqa: E402
+from oracle import dsp_oracle as o            # noqa: E402
+
+clips = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
+variants = [int(v) for v in sys.argv[2:]] or list(range(8))
+n, n_fft = 480000, 4096
+torch.cuda.set_device(0)
+plan = pkg.FftPlan(n_fft, np.float32, hann=True)
+rng = np.random.default_rng(3)
+xs = rng.uniform(-1, 1, (4, 3 * n_fft + 100)).astype(np.float32)
+xs_d = torch.as_tensor(xs, device="cuda")
+ref = np.stack([[o.magnitude_frames(xs[c].astype(np.float64), n_fft)[f] for f in range(3)] for c in range(4)]) \
+    if hasattr(o, "magnitude_frames") else None
+if ref is None:
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / (n_fft - 1))
+    ref = np.abs(np.fft.rfft(xs[:, :3 * n_fft].astype(np.float64).reshape(4, 3, n_fft) * w, axis=-1))
+x = torch.empty((clips, n), dtype=torch.float32, device="cuda").uniform_(-1, 1)
+out = torch.empty((clips, plan.n_frames(n), plan.bins), dtype=torch.float32, device="cuda")
+alg = x.numel() * 4 + out.numel() * 4
+for v in variants:
+    os.environ["DSPB200_FFT_VAR"] = str(v)
+    m = plan.magnitudes(xs_d).cpu().numpy().astype(np.float64)
+    err = float(np.max(np.abs(m - ref)) / np.max(np.abs(ref)))
+    for _ in range(3):
+        plan.magnitudes(x, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        plan.magnitudes(x, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(json.dumps({"var": v, "clips": clips, "ms": round(ms, 4), "gbs": round(alg / ms / 1e6, 1),
+                      "err_full_scale": err}), flush=True)
