@@ -13,7 +13,7 @@ import dsp_audio_project_b200 as pkg          # noqa: E402
 from oracle import dsp_oracle as o            # noqa: E402
 
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
-variants = [int(v) for v in sys.argv[2:]] or list(range(8))
+variants = sys.argv[2:] or ["0", "6", "7", "15"]     # "var[:cNN][:mK]": shared-memory carve-out %, CTA cap per SM
 n, n_fft = 480000, 4096
 torch.cuda.set_device(0)
 plan = pkg.FftPlan(n_fft, np.float32, hann=True)
@@ -29,7 +29,12 @@ x = torch.empty((clips, n), dtype=torch.float32, device="cuda").uniform_(-1, 1)
 out = torch.empty((clips, plan.n_frames(n), plan.bins), dtype=torch.float32, device="cuda")
 alg = x.numel() * 4 + out.numel() * 4
 for v in variants:
-    os.environ["DSPB200_FFT_VAR"] = str(v)
+    parts = str(v).split(":")
+    os.environ["DSPB200_FFT_VAR"] = parts[0]
+    os.environ.pop("DSPB200_FFT_CARVEOUT", None)
+    os.environ.pop("DSPB200_FFT_MAX_CTAS", None)
+    for q in parts[1:]:
+        os.environ["DSPB200_FFT_CARVEOUT" if q[0] == "c" else "DSPB200_FFT_MAX_CTAS"] = q[1:]
     m = plan.magnitudes(xs_d).cpu().numpy().astype(np.float64)
     err = float(np.max(np.abs(m - ref)) / np.max(np.abs(ref)))
     for _ in range(3):
