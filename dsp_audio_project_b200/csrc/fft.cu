@@ -470,13 +470,20 @@ fft_fixed_kernel(const FftArgs<T> a) {
   }
 
   // raw operands of one item, all 16 loads in flight (no window yet)
-  auto fetch = [&](long long item, C* tmp) {
-    const long long fl = item / a.r_top;
-    const int rho = static_cast<int>(item - fl * a.r_top);
+  auto fetch = [&](long long item, C* tmp, long long c_item, long long fr_item) {
+    long long fl = item;
+    int rho = 0;
+    if constexpr (kSplit) {
+      fl = item / a.r_top;
+      rho = static_cast<int>(item - fl * a.r_top);
+    }
     const long long f = a.first + fl;
     if constexpr (kReal) {
-      const long long c = f / a.n_frames;
-      const long long fr = f - c * a.n_frames;
+      long long c = c_item, fr = fr_item;
+      if constexpr (kSplit) {
+        c = f / a.n_frames;
+        fr = f - c * a.n_frames;
+      }
       const T* xrow = a.x + c * a.x_stride;
       const long long fstart = a.offset + fr * a.hop;
       const bool fast = (fstart + 2LL * a.nc <= a.n_valid) &&
@@ -525,15 +532,30 @@ fft_fixed_kernel(const FftArgs<T> a) {
     }
   }
   C tmp[16];
-  if (blockIdx.x < a.n_items) fetch(blockIdx.x, tmp);
+  // (channel, frame) of the item in flight, advanced by the grid stride without a 64-bit division per frame
+  long long c_next = 0, fr_next = 0, dc = 0, dfr = 0;
+  if constexpr (kReal && !kSplit) {
+    const long long f0 = a.first + blockIdx.x;
+    c_next = f0 / a.n_frames;
+    fr_next = f0 - c_next * a.n_frames;
+    dc = static_cast<long long>(gridDim.x) / a.n_frames;
+    dfr = static_cast<long long>(gridDim.x) - dc * a.n_frames;
+  }
+  if (blockIdx.x < a.n_items) fetch(blockIdx.x, tmp, c_next, fr_next);
   for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-    const long long fl = item / a.r_top;
-    const int rho = static_cast<int>(item - fl * a.r_top);
+    long long fl = item;
+    int rho = 0;
+    if constexpr (kSplit) {
+      fl = item / a.r_top;
+      rho = static_cast<int>(item - fl * a.r_top);
+    }
     const long long f = a.first + fl;
-    long long c = 0, fr = 0;
+    long long c = c_next, fr = fr_next;
     if constexpr (kReal) {
-      c = f / a.n_frames;
-      fr = f - c * a.n_frames;
+      if constexpr (kSplit) {
+        c = f / a.n_frames;
+        fr = f - c * a.n_frames;
+      }
       if constexpr (kHannFly) {
         if (a.window) {
           const C half = {T(0.5), T(0.5)};
@@ -559,7 +581,14 @@ fft_fixed_kernel(const FftArgs<T> a) {
     __syncthreads();   // previous item's readers are done with s
     ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t);
     // the next item's loads fly while this item's epilogue reads shared memory
-    if (item + gridDim.x < a.n_items) fetch(item + gridDim.x, tmp);
+    if (item + gridDim.x < a.n_items) {
+      if constexpr (kReal && !kSplit) {
+        fr_next += dfr;
+        c_next += dc;
+        if (fr_next >= a.n_frames) { fr_next -= a.n_frames; ++c_next; }
+      }
+      fetch(item + gridDim.x, tmp, c_next, fr_next);
+    }
     if constexpr (MODE == 0) {
       T* mg = a.mag + c * a.mag_channel_stride + fr * a.mag_frame_stride;
       constexpr int NC = M;   // r_top == 1

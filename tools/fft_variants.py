@@ -28,24 +28,29 @@ if ref is None:
 x = torch.empty((clips, n), dtype=torch.float32, device="cuda").uniform_(-1, 1)
 out = torch.empty((clips, plan.n_frames(n), plan.bins), dtype=torch.float32, device="cuda")
 alg = x.numel() * 4 + out.numel() * 4
-for v in variants:
-    parts = str(v).split(":")
-    os.environ["DSPB200_FFT_VAR"] = parts[0]
-    os.environ.pop("DSPB200_FFT_CARVEOUT", None)
-    os.environ.pop("DSPB200_FFT_MAX_CTAS", None)
-    for q in parts[1:]:
-        os.environ["DSPB200_FFT_CARVEOUT" if q[0] == "c" else "DSPB200_FFT_MAX_CTAS"] = q[1:]
-    m = plan.magnitudes(xs_d).cpu().numpy().astype(np.float64)
-    err = float(np.max(np.abs(m - ref)) / np.max(np.abs(ref)))
-    for _ in range(3):
-        plan.magnitudes(x, out=out)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        plan.magnitudes(x, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(json.dumps({"var": v, "clips": clips, "ms": round(ms, 4), "gbs": round(alg / ms / 1e6, 1),
+best = {}
+for rnd in range(3):                       # interleaved rounds, best of each: the clock drifts under the power cap
+    for v in variants:
+        parts = str(v).split(":")
+        os.environ["DSPB200_FFT_VAR"] = parts[0]
+        os.environ.pop("DSPB200_FFT_CARVEOUT", None)
+        os.environ.pop("DSPB200_FFT_MAX_CTAS", None)
+        for q in parts[1:]:
+            os.environ["DSPB200_FFT_CARVEOUT" if q[0] == "c" else "DSPB200_FFT_MAX_CTAS"] = q[1:]
+        m = plan.magnitudes(xs_d).cpu().numpy().astype(np.float64)
+        err = float(np.max(np.abs(m - ref)) / np.max(np.abs(ref)))
+        for _ in range(2):
+            plan.magnitudes(x, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            plan.magnitudes(x, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        if v not in best or ms < best[v][0]:
+            best[v] = (ms, err)
+for v, (ms, err) in best.items():
+    print(json.dumps({"var": v, "clips": clips, "ms_best_of_3": round(ms, 4), "gbs": round(alg / ms / 1e6, 1),
                       "err_full_scale": err}), flush=True)
