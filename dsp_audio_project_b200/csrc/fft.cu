@@ -23,7 +23,9 @@
 // real split and the magnitude.
 //
 // Twiddles are float64-accurate tables rounded to the working type (the
-// reference evaluates np.exp per level, dsp_core.py:59-60), never recurrences.
+// reference evaluates np.exp per level, dsp_core.py:59-60), never recurrences;
+// the fp32 magnitude kernel and the four-step form derive some powers from
+// table entries by product trees at most 3-4 roundings deep.
 //
 // Roofline (per frame of N real samples): N*sizeof(T) bytes read +
 // (N/2+1)*sizeof(T) written; ~2.5 N log2 N flop.
