@@ -219,3 +219,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no CPU fallback", ""), f
+
+
+@pytest.mark.parametrize("n_fft", [1024, 4096, 16384])
+def test_hann_by_angle_addition_matches_the_reference_window(n_fft):
+    """The fp32 magnitude kernel forms the reference's symmetric Hann (dsp_core.py:85-87) as
+    1/2 + A_t cos(u D) + B_t sin(u D) for the samples n = 2(t + uQ) + {0,1} a thread owns (csrc/fft.cu,
+    plan_build); the same arithmetic in float32 stays within 2e-7 of the float64 window."""
+    m = n_fft // 2
+    q = m // 16
+    step = 2.0 * np.pi / (n_fft - 1)
+    t = np.arange(q)[:, None, None]
+    h = np.arange(2)[None, None, :]
+    u = np.arange(16)[None, :, None]
+    phi = step * (2 * t + h)
+    a = (-0.5 * np.cos(phi)).astype(np.float32)
+    b = (0.5 * np.sin(phi)).astype(np.float32)
+    cc = np.cos(step * 2 * q * u).astype(np.float32)
+    ss = np.sin(step * 2 * q * u).astype(np.float32)
+    w = (a * cc + (b * ss + np.float32(0.5))).astype(np.float32)       # two fused multiply-adds in the kernel
+    n = (2 * (t + u * q) + h).reshape(-1)
+    ref = o.hann_symmetric(n_fft)
+    assert sorted(n.tolist()) == list(range(n_fft))
+    assert np.max(np.abs(w.reshape(-1).astype(np.float64) - ref[n])) <= 2e-7

@@ -318,6 +318,36 @@ def test_fftmag_frames_vs_oracle(pk, torch_cuda, n_fft):
             assert o.rel_err(m2[:, f], r2) <= tol
 
 
+@pytest.mark.parametrize("n_fft", [2048, 4096])
+def test_fftmag_many_frames_grid_stride(pk, torch_cuda, n_fft, monkeypatch):
+    """More frames than resident CTAs: every CTA walks several (channel, frame) items, which the fp32
+    magnitude kernel tracks by grid-stride carries instead of divisions; 41 x 47 frames make the carry
+    fire at irregular steps.  Also pins the kernel variants (DSPB200_FFT_VAR: 0 = table Hann/twiddles,
+    15 = six CTAs per SM) and the dB store against the same reference."""
+    torch = torch_cuda
+    rng = np.random.default_rng(7 + n_fft)
+    channels, n_frames = 41, 47
+    x = rng.uniform(-1, 1, (channels, n_fft * n_frames + 5)).astype(np.float32)
+    w = o.hann_symmetric(n_fft)
+    ref = np.abs(np.fft.rfft(x[:, :n_fft * n_frames].astype(np.float64).reshape(channels, n_frames, n_fft) * w, axis=-1))
+    xt = torch.as_tensor(x, device="cuda")
+    plan = pk.FftPlan(n_fft, np.float32, hann=True)
+    for var in (None, "0", "15"):
+        if var is None:
+            monkeypatch.delenv("DSPB200_FFT_VAR", raising=False)
+        else:
+            monkeypatch.setenv("DSPB200_FFT_VAR", var)
+        mag = plan.magnitudes(xt).cpu().numpy()
+        assert mag.shape == ref.shape
+        err = np.max(np.abs(mag - ref), axis=-1) / np.max(np.abs(ref), axis=-1)
+        assert err.max() <= TOL_F32_FFT, (var, float(err.max()), np.unravel_index(err.argmax(), err.shape))
+    monkeypatch.delenv("DSPB200_FFT_VAR", raising=False)
+    db = pk.FftPlan(n_fft, np.float32, hann=True, db=True).magnitudes(xt).cpu().numpy()
+    ref_db = 20.0 * np.log10(ref + 1e-12)
+    loud = ref > 1e-3 * ref.max()
+    assert np.max(np.abs(db - ref_db)[loud]) <= 1e-3          # dB of values within 1e-5 of full scale
+
+
 def test_fft_parseval_and_linearity_full_c4_frame_count(pk, torch_cuda):
     """A slice of C4 (2^16-point frames of 2^20-sample clips): 64 channels x 16
     frames, fp32 -- Parseval against the time-domain energy of each frame."""
