@@ -68,6 +68,7 @@ SIGNATURES = {
     "dspb200_chain_workspace_bytes": (C.c_int, [c_p, c_p, c_i64, c_i64, C.c_int, C.POINTER(C.c_size_t)]),
     "dspb200_chain_run_f32": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
     "dspb200_chain_run_f64": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
+    "dspb200_chain_kernel_kind": (C.c_int, [c_p, c_p, c_i64, c_i64, c_i64, _pi]),
     "dspb200_chain_host_f32": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dspb200_chain_host_f64": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dspb200_host_release": (C.c_int, []),
@@ -82,6 +83,7 @@ EXTRA_SIGNATURES = {
     "dspb200_src_run_generic_f32": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_src_run_generic_f64": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_src_run_tiled_f32": (C.c_int, [c_p, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
+    "dspb200_chain_fused_f32": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_i64, c_p]),
 }
 
 _lib = None

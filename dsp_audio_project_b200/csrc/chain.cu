@@ -16,6 +16,12 @@ static int64_t src_out_len(int L, int M, int64_t n_in) {
   return n_out;
 }
 
+static int64_t src_out_len_of(const dspb200_src_plan* src, int64_t n_in) {
+  int L = 1, M = 1, dt = 0;
+  if (src_plan_ratio(src, &L, &M, &dt) != DSPB200_OK) return 0;
+  return src_out_len(L, M, n_in);
+}
+
 struct ChainShape {
   int L = 1, M = 1, n_fft = 0;
   int64_t n_out = 0, n_frames = 0, bins = 0;
@@ -46,6 +52,24 @@ static int chain_shape(const dspb200_src_plan* src, const dspb200_fft_plan* fft,
   return DSPB200_OK;
 }
 
+// Would a cascade of this shape run SRC and EQ as the one fused kernel (xz_mma.cu)?  *xp is NULL when not.
+template <typename T>
+static int chain_fused_plan(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const T* x, int64_t xs, const T* z,
+                            int64_t zs, int64_t channels, int64_t n_in, bool force, const XzPlan** xp) {
+  *xp = nullptr;
+  if (sizeof(T) != 4 || !src || !eq || getenv("DSPB200_CHAIN_NO_FUSED") != nullptr) return DSPB200_OK;
+  const XzPlan* p = nullptr;
+  DSP_TRY(eq_plan_xz(eq, src, &p));
+  if (!p) return DSPB200_OK;
+  const std::vector<double>* taps = src_plan_taps(src);
+  const int n_taps = taps ? static_cast<int>(taps->size()) : 0;
+  const float* xf = reinterpret_cast<const float*>(x);
+  const float* zf = reinterpret_cast<const float*>(z);
+  const bool ok = force ? xz_possible(*p, xf, xs, zf, zs, n_in, n_taps) : xz_usable(*p, xf, xs, zf, zs, channels, n_in, n_taps);
+  if (ok) *xp = p;
+  return DSPB200_OK;
+}
+
 template <typename T>
 static int chain_run(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
                      const T* x, int64_t xs, int64_t channels, int64_t n_in, T* y, T* z, T* mag, void* ws,
@@ -55,32 +79,35 @@ static int chain_run(const dspb200_src_plan* src, const dspb200_eq_plan* eq, con
   DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
   ChainShape s;
   DSP_TRY(chain_shape<T>(src, fft, channels, n_in, s));
+  if (eq) DSP_CHECK(eq_plan_dtype(eq) == DType<T>::id, "eq plan dtype does not match");
   unsigned char* wsp = static_cast<unsigned char*>(ws);
-  size_t used = 0;
-  const T* yp = x;
-  int64_t y_stride = xs;
-  if (src) {
-    T* ybuf = y;
-    if (!ybuf) {
-      DSP_CHECK(ws != nullptr && ws_bytes >= s.y_bytes, "workspace too small for the SRC scratch");
-      ybuf = reinterpret_cast<T*>(wsp);
-      used = s.y_bytes;
-    }
-    DSP_TRY(src_run<T>(src, x, xs, ybuf, s.n_out, channels, n_in, stream, -1));
-    yp = ybuf;
-    y_stride = s.n_out;
-  }
-  if (eq) {
-    DSP_CHECK(eq_plan_dtype(eq) == DType<T>::id, "eq plan dtype does not match");
-    DSP_TRY(eq_run<T>(eq, yp, y_stride, z, s.n_out, channels, s.n_out, stream));
+  const XzPlan* xp = nullptr;
+  if (!y) DSP_TRY(chain_fused_plan<T>(src, eq, x, xs, z, s.n_out, channels, n_in, false, &xp));
+  if (xp) {
+    // SRC and EQ as one kernel: x is read once, z written once, y never exists (app.py:164-167)
+    DSP_TRY(xz_run(*xp, reinterpret_cast<const float*>(x), xs, reinterpret_cast<float*>(z), s.n_out, channels, n_in, s.n_out,
+                   eq_plan_clip(eq) != 0, stream));
   } else {
-    DSP_CUDA(cudaMemcpy2DAsync(z, s.n_out * sizeof(T), yp, y_stride * sizeof(T), s.n_out * sizeof(T), channels,
-                               cudaMemcpyDeviceToDevice, stream));
+    const T* yp = x;
+    int64_t y_stride = xs;
+    if (src) {
+      // without a caller-provided y the resampler writes into z and the equaliser runs in place: no scratch
+      T* ybuf = y ? y : z;
+      DSP_TRY(src_run<T>(src, x, xs, ybuf, s.n_out, channels, n_in, stream, -1));
+      yp = ybuf;
+      y_stride = s.n_out;
+    }
+    if (eq) {
+      DSP_TRY(eq_run<T>(eq, yp, y_stride, z, s.n_out, channels, s.n_out, stream));
+    } else if (yp != z) {
+      DSP_CUDA(cudaMemcpy2DAsync(z, s.n_out * sizeof(T), yp, y_stride * sizeof(T), s.n_out * sizeof(T), channels,
+                                 cudaMemcpyDeviceToDevice, stream));
+    }
   }
   if (fft && mag && s.n_frames > 0) {
-    DSP_CHECK(s.fft_ws == 0 || (ws != nullptr && ws_bytes >= used + s.fft_ws), "workspace too small for the FFT");
+    DSP_CHECK(s.fft_ws == 0 || (ws != nullptr && ws_bytes >= s.fft_ws), "workspace too small for the FFT");
     DSP_TRY(fftmag_run<T>(fft, z, s.n_out, s.n_out, 0, s.n_fft, s.n_frames, mag, s.bins, s.n_frames * s.bins,
-                          channels, wsp ? wsp + used : nullptr, s.fft_ws, stream));
+                          channels, wsp, s.fft_ws, stream));
   }
   return DSPB200_OK;
 }
@@ -144,7 +171,7 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
   T* dz[kStreams] = {nullptr, nullptr, nullptr};
   T* dm[kStreams] = {nullptr, nullptr, nullptr};
   void* dw[kStreams] = {nullptr, nullptr, nullptr};
-  const size_t ws_bytes = s.y_bytes + s.fft_ws;
+  const size_t ws_bytes = s.fft_ws;
   const size_t mag_elems = static_cast<size_t>(slab) * s.n_frames * s.bins;
   cudaError_t e = cudaSuccess;
   int rc = DSPB200_OK;
@@ -203,7 +230,8 @@ int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_fft
   ChainShape s;
   if (dtype == DSPB200_F32) DSP_TRY(chain_shape<float>(src, fft, channels, n_in, s));
   else DSP_TRY(chain_shape<double>(src, fft, channels, n_in, s));
-  *bytes = ((src && !keep_y) ? s.y_bytes : 0) + s.fft_ws;
+  (void)keep_y;   // no y scratch any more: without a y buffer the resampler writes into z and the equaliser runs in place
+  *bytes = s.fft_ws;
   return DSPB200_OK;
 }
 
@@ -218,6 +246,33 @@ int dspb200_chain_run_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq
                           double* mag, void* ws, size_t ws_bytes, void* stream) {
   return chain_run<double>(src, eq, fft, x, xs, channels, n_in, y, z, mag, ws, ws_bytes,
                            static_cast<cudaStream_t>(stream));
+}
+int dspb200_chain_kernel_kind(const dspb200_src_plan* src, const dspb200_eq_plan* eq, int64_t channels, int64_t n_in,
+                              int64_t x_stride, int* kind) {
+  DSP_CHECK(kind != nullptr, "kind is NULL");
+  *kind = 0;
+  if (!src || !eq) return DSPB200_OK;
+  DSP_TRY(ensure_device());
+  const XzPlan* xp = nullptr;
+  const int64_t n_out = src_out_len_of(src, n_in);
+  DSP_TRY(chain_fused_plan<float>(src, eq, nullptr, x_stride, nullptr, n_out, channels, n_in, false, &xp));
+  *kind = xp ? 1 : 0;
+  return DSPB200_OK;
+}
+/* test hook: the fused SRC->EQ kernel whatever the batch width; DSPB200_ERR_UNSUPPORTED when the pair has no fused form */
+int dspb200_chain_fused_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const float* x, int64_t xs,
+                            int64_t channels, int64_t n_in, float* z, int64_t zs, void* stream) {
+  DSP_CHECK(src != nullptr && eq != nullptr, "NULL plan");
+  DSP_CHECK(channels >= 0 && n_in >= 1, "bad shape");
+  if (channels == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
+  DSP_TRY(ensure_device());
+  const XzPlan* xp = nullptr;
+  DSP_TRY(chain_fused_plan<float>(src, eq, x, xs, z, zs, channels, n_in, true, &xp));
+  if (!xp) return fail(DSPB200_ERR_UNSUPPORTED, "no fused SRC->EQ form for this plan pair / alignment");
+  const int64_t n_out = src_out_len_of(src, n_in);
+  DSP_CHECK(xs >= n_in && zs >= n_out, "channel stride smaller than the row length");
+  return xz_run(*xp, x, xs, z, zs, channels, n_in, n_out, eq_plan_clip(eq) != 0, static_cast<cudaStream_t>(stream));
 }
 int dspb200_chain_host_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
                            const float* x, int64_t channels, int64_t n_in, float* z, float* mag) {

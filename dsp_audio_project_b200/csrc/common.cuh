@@ -48,6 +48,19 @@ inline int after_launch(const char* what) {
   return DSPB200_OK;
 }
 
+// Every plan struct starts with a type tag: an entry point handed the wrong (or a destroyed) handle answers
+// DSPB200_ERR_INVALID instead of reading another plan's layout.  Plans that own device tables also record the
+// device they were built on; running them with another device current is an error, not a stray pointer.
+constexpr uint32_t kMagicSrc = 0x31435253u;   // "SRC1"
+constexpr uint32_t kMagicEq = 0x31205145u;    // "EQ 1"
+constexpr uint32_t kMagicFft = 0x31544646u;   // "FFT1"
+#define DSP_PLAN(p, MAGIC, what)                                                                    \
+  do {                                                                                              \
+    DSP_CHECK((p) != nullptr, what " plan is NULL");                                                \
+    DSP_CHECK((p)->magic == (MAGIC), "handle %p is not a live " what " plan", (const void*)(p));    \
+  } while (0)
+int check_plan_device(int plan_device, const char* what);   // plan_device < 0: the plan owns no device memory
+
 int ensure_device();            // checks a usable sm_100 device is current
 int sm_count();                 // SMs of the current device (cached per device)
 int max_smem_optin();           // opt-in shared memory per block
@@ -65,6 +78,9 @@ int encode_tmap_2d(CUtensorMap* map, int dtype, const void* base, uint64_t dim0,
                    uint64_t stride1_bytes, uint32_t box0, uint32_t box1, bool swizzle128 = false);
 int encode_tmap_2d_sw(CUtensorMap* map, int dtype, const void* base, uint64_t dim0, uint64_t dim1,
                       uint64_t stride1_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes);   // 0, 64 or 128
+constexpr int kTmapF16 = 16;   // internal dtype code of encode_tmap_2d_sw: fp16 tables of the fused chain kernel
+int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                       uint32_t box0, uint32_t box1);                                              // 128-byte swizzle
 
 #ifdef __CUDACC__
 // ---- device utilities ----------------------------------------------------

@@ -65,6 +65,16 @@ int ensure_device() {
   return DSPB200_OK;
 }
 
+int check_plan_device(int plan_device, const char* what) {
+  if (plan_device < 0) return DSPB200_OK;
+  int dev = -1;
+  DSP_CUDA(cudaGetDevice(&dev));
+  if (dev != plan_device)
+    return fail(DSPB200_ERR_INVALID, "%s plan was built on device %d but device %d is current: its tables live on device %d",
+                what, plan_device, dev, plan_device);
+  return DSPB200_OK;
+}
+
 int sm_count() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -106,13 +116,20 @@ int encode_tmap_2d_sw(CUtensorMap* map, int dtype, const void* base, uint64_t di
   cuuint64_t strides[1] = {stride1_bytes};
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, dtype == DSPB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+  const CUtensorMapDataType dt = dtype == DSPB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+                                 : (dtype == kTmapF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult r = fn(map, dt,
                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(DSPB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return DSPB200_OK;
+}
+
+int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                       uint32_t box0, uint32_t box1) {
+  return encode_tmap_2d_sw(map, kTmapF16, base, dim0, dim1, stride1_bytes, box0, box1, 128);
 }
 
 }  // namespace dspb200

@@ -477,6 +477,7 @@ eq_packed_kernel(const __grid_constant__ EqPackedParams p, const float* __restri
 }  // namespace dspb200
 
 struct dspb200_eq_plan {
+  uint32_t magic = dspb200::kMagicEq;   // first member: checked by every entry point
   int dtype;
   int clip;
   int device;
@@ -486,6 +487,9 @@ struct dspb200_eq_plan {
   int mma_state = 0;   // 0 not tried, 1 built, -1 not available
   int mma_device = -1;
   dspb200::LtiMmaPlan mma;
+  // fused SRC->EQ form (xz_mma.cu) for the resampler ratio it was last asked for; same lazy construction
+  int xz_state = 0, xz_L = 0, xz_M = 0;
+  dspb200::XzPlan xz;
 };
 
 namespace dspb200 {
@@ -670,7 +674,7 @@ static int eq_mma_ready(const dspb200_eq_plan* plan, const float* x, int64_t xs,
 template <typename T>
 int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs, int64_t channels,
            int64_t n, cudaStream_t stream) {
-  DSP_CHECK(plan != nullptr, "plan is NULL");
+  DSP_PLAN(plan, kMagicEq, "eq");
   DSP_CHECK(plan->dtype == DType<T>::id, "plan dtype %d does not match the entry point", plan->dtype);
   DSP_CHECK(channels >= 0 && n >= 0, "negative shape");
   if (channels == 0 || n == 0) return DSPB200_OK;
@@ -714,11 +718,40 @@ int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs
 template int eq_run<float>(const dspb200_eq_plan*, const float*, int64_t, float*, int64_t, int64_t, int64_t, cudaStream_t);
 template int eq_run<double>(const dspb200_eq_plan*, const double*, int64_t, double*, int64_t, int64_t, int64_t, cudaStream_t);
 
-int eq_plan_dtype(const dspb200_eq_plan* plan) { return plan ? plan->dtype : -1; }
+int eq_plan_clip(const dspb200_eq_plan* plan) { return (plan && plan->magic == kMagicEq) ? plan->clip : 0; }
+
+int eq_plan_xz(const dspb200_eq_plan* eq, const dspb200_src_plan* src, const XzPlan** xp) {
+  *xp = nullptr;
+  DSP_PLAN(eq, kMagicEq, "eq");
+  const std::vector<double>* taps = src_plan_taps(src);
+  DSP_CHECK(taps != nullptr, "handle is not a live src plan");
+  int L = 0, M = 0, dt = 0;
+  DSP_TRY(src_plan_ratio(src, &L, &M, &dt));
+  const int total = static_cast<int>(eq->sections.size());
+  if (eq->dtype != DSPB200_F32 || dt != DSPB200_F32 || total < 1 || total > kLtiMaxStates / 2) return DSPB200_OK;
+  int dev = 0;
+  DSP_CUDA(cudaGetDevice(&dev));
+  dspb200_eq_plan* mp = const_cast<dspb200_eq_plan*>(eq);
+  std::lock_guard<std::mutex> lk(mp->mma_mu);
+  if (mp->xz_state != 0 && (mp->xz_L != L || mp->xz_M != M || (mp->xz_state == 1 && mp->xz.device != dev))) {
+    if (mp->xz_state == 1) xz_free(mp->xz);
+    mp->xz_state = 0;
+  }
+  if (mp->xz_state == 0) {
+    DSP_TRY(xz_build(*taps, L, M, mp->sections.data(), total, mp->xz));
+    mp->xz_state = mp->xz.ok ? 1 : -1;
+    mp->xz_L = L;
+    mp->xz_M = M;
+  }
+  if (mp->xz_state == 1) *xp = &mp->xz;
+  return DSPB200_OK;
+}
+
+int eq_plan_dtype(const dspb200_eq_plan* plan) { return (plan && plan->magic == kMagicEq) ? plan->dtype : -1; }
 
 template <typename T>
 static int eq_host(const dspb200_eq_plan* plan, const T* x, T* z, int64_t channels, int64_t n) {
-  DSP_CHECK(plan != nullptr, "plan is NULL");
+  DSP_PLAN(plan, kMagicEq, "eq");
   DSP_CHECK(channels >= 0 && n >= 0, "negative shape");
   if (channels == 0 || n == 0) return DSPB200_OK;
   DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
@@ -801,14 +834,19 @@ int dspb200_eq_plan_create_bands(double fs, const double gains_db[DSPB200_EQ_BAN
 }
 
 int dspb200_eq_plan_destroy(dspb200_eq_plan* plan) {
-  if (plan && plan->mma_state == 1) lti_mma_free(plan->mma);
+  if (!plan) return DSPB200_OK;
+  DSP_PLAN(plan, kMagicEq, "eq");
+  plan->magic = 0;
+  if (plan->mma_state == 1) lti_mma_free(plan->mma);
+  if (plan->xz_state == 1) xz_free(plan->xz);
   delete plan;
   return DSPB200_OK;
 }
 
 int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, int64_t n, int64_t x_stride,
                                 int* kind) {
-  DSP_CHECK(plan != nullptr && kind != nullptr, "NULL argument");
+  DSP_PLAN(plan, kMagicEq, "eq");
+  DSP_CHECK(kind != nullptr, "NULL argument");
   DSP_TRY(ensure_device());
   bool tensor = false;
   DSP_TRY(eq_mma_ready(plan, nullptr, x_stride, nullptr, x_stride, channels, n, tensor));
@@ -818,7 +856,8 @@ int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, i
 
 int dspb200_eq_plan_chunk_system(const dspb200_eq_plan* plan, int* rows, int* states, double* tk, double* o,
                                  double* phi) {
-  DSP_CHECK(plan != nullptr && rows != nullptr && states != nullptr, "NULL argument");
+  DSP_PLAN(plan, kMagicEq, "eq");
+  DSP_CHECK(rows != nullptr && states != nullptr, "NULL argument");
   LtiChunkSystem cs;
   DSP_TRY(lti_chunk_system(plan->sections.data(), static_cast<int>(plan->sections.size()), cs));
   *rows = cs.rows;
@@ -831,7 +870,8 @@ int dspb200_eq_plan_chunk_system(const dspb200_eq_plan* plan, int* rows, int* st
 }
 
 int dspb200_eq_plan_describe(const dspb200_eq_plan* plan, int* n_sections, double* ss, int capacity) {
-  DSP_CHECK(plan != nullptr && n_sections != nullptr, "NULL argument");
+  DSP_PLAN(plan, kMagicEq, "eq");
+  DSP_CHECK(n_sections != nullptr, "NULL argument");
   *n_sections = static_cast<int>(plan->sections.size());
   for (int i = 0; i < *n_sections && i < capacity && ss; ++i) {
     const Section& s = plan->sections[static_cast<size_t>(i)];
@@ -854,7 +894,8 @@ int dspb200_eq_stream_chunk(void) { return lti_mma_chunk(); }
 
 int dspb200_eq_run_stream_f32(const dspb200_eq_plan* plan, const float* x, int64_t xs, float* z, int64_t zs,
                               int64_t channels, int64_t n, float* state, int first, void* stream) {
-  DSP_CHECK(plan != nullptr && state != nullptr, "NULL argument");
+  DSP_PLAN(plan, kMagicEq, "eq");
+  DSP_CHECK(state != nullptr, "NULL argument");
   DSP_CHECK(plan->dtype == DSPB200_F32, "the streaming form is float32 only");
   DSP_CHECK(channels >= 0 && n >= 0, "negative shape");
   if (channels == 0 || n == 0) return DSPB200_OK;
@@ -871,11 +912,13 @@ int dspb200_eq_run_stream_f32(const dspb200_eq_plan* plan, const float* x, int64
 }
 
 int dspb200_eq_host_f32(const dspb200_eq_plan* plan, const float* x, float* z, int64_t channels, int64_t n) {
-  DSP_CHECK(plan && plan->dtype == DSPB200_F32, "plan is NULL or not float32");
+  DSP_PLAN(plan, kMagicEq, "eq");
+  DSP_CHECK(plan->dtype == DSPB200_F32, "plan is not float32");
   return eq_host<float>(plan, x, z, channels, n);
 }
 int dspb200_eq_host_f64(const dspb200_eq_plan* plan, const double* x, double* z, int64_t channels, int64_t n) {
-  DSP_CHECK(plan && plan->dtype == DSPB200_F64, "plan is NULL or not float64");
+  DSP_PLAN(plan, kMagicEq, "eq");
+  DSP_CHECK(plan->dtype == DSPB200_F64, "plan is not float64");
   return eq_host<double>(plan, x, z, channels, n);
 }
 

@@ -40,6 +40,7 @@
 
 #include "design.cuh"
 #include "internal.cuh"
+#include "umma.cuh"
 
 namespace dspb200 {
 
@@ -90,56 +91,7 @@ struct LtiArgs {
   float phi[kLtiMaxStates * kLtiMaxStates];
 };
 
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* p) {
-  // K-major operand, 128-byte swizzle: 8-row groups 1024 bytes apart, descriptor version 1 (sm_100)
-  const uint64_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p));
-  return ((addr >> 4) & 0x3FFF) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
-  // A operand in tensor memory (row = lane, one tf32 per column), B through its shared-memory descriptor
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
-               ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-               ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t* v, uint32_t taddr) {   // 32 lanes x 16 columns, one column per register
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float clip_unit(float y) {   // NaN passes through like np.clip
-  float r;
-  asm("max.NaN.f32 %0, %1, 0fBF800000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(r) : "f"(y));
-  return r;
-}
-__device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // s <- Phi s + u.  Phi sits in the kernel parameters: every FFMA takes its coefficient from the constant bank.
 template <int kS>
@@ -539,10 +491,12 @@ void cascade_state_space(const Section* sec, int ns, std::vector<double>& A, std
   }
 }
 
-// The chunk system of a cascade in float64 (host only): z = T x + O s, s' = Phi s + K x over kRows samples, states
+// The chunk system of a cascade in float64 (host only): z = T x + O s, s' = Phi s + K x over `rows` samples (0: the
+// tensor-core EQ's 96), states
 // rescaled to unit row norms of K so that every state row of the GEMM is computed at full relative precision.
-int lti_chunk_system(const Section* sec, int ns, LtiChunkSystem& cs) {
+int lti_chunk_system(const Section* sec, int ns, LtiChunkSystem& cs, int rows) {
   cs = LtiChunkSystem{};
+  const int kRows = rows > 0 ? rows : dspb200::kRows;   // shadows the tensor-core EQ's chunk length
   if (ns < 1 || 2 * ns > kLtiMaxStates) return DSPB200_OK;
   const int n = 2 * ns;
   std::vector<double> A, B, C;

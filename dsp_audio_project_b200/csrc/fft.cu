@@ -919,6 +919,7 @@ struct FftSide {
 }  // namespace dspb200
 
 struct dspb200_fft_plan {
+  uint32_t magic = dspb200::kMagicFft;   // first member: checked by every entry point
   int n_fft, hann, db, dtype, device;
   dspb200::FftSide real_side, c2c_side;
   dspb200::FftSide fs_cols, fs_rows;   // four-step form of a long real transform: N1-point columns, 128-point rows
@@ -1254,13 +1255,14 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
                int64_t n_frames, T* mag, int64_t mfs, int64_t mcs, int64_t channels, void* ws, size_t ws_bytes,
                cudaStream_t stream) {
   typedef typename Cpx<T>::type C;
-  DSP_CHECK(p != nullptr, "plan is NULL");
+  DSP_PLAN(p, kMagicFft, "fft");
   DSP_CHECK(p->dtype == DType<T>::id, "plan dtype %d does not match the entry point", p->dtype);
   DSP_CHECK(channels >= 0 && n_frames >= 0 && n_valid >= 0 && offset >= 0 && hop >= 0, "negative argument");
   if (channels == 0 || n_frames == 0) return DSPB200_OK;
   DSP_CHECK(x != nullptr && mag != nullptr, "NULL buffer");
   DSP_CHECK(mfs >= p->n_fft / 2 + 1, "mag_frame_stride smaller than n_fft/2+1");
   DSP_TRY(ensure_device());
+  DSP_TRY(check_plan_device(p->device, "fft"));
   const int64_t n_tr = channels * n_frames;
   FftArgs<T> a{};
   a.x = x; a.x_stride = xs; a.n_valid = n_valid; a.offset = offset; a.hop = hop; a.n_frames = n_frames;
@@ -1330,13 +1332,14 @@ template <typename T>
 int fft_c2c_run(const dspb200_fft_plan* p, const T* in, T* out, int64_t batch, void* ws, size_t ws_bytes,
                 cudaStream_t stream) {
   typedef typename Cpx<T>::type C;
-  DSP_CHECK(p != nullptr, "plan is NULL");
+  DSP_PLAN(p, kMagicFft, "fft");
   DSP_CHECK(p->dtype == DType<T>::id, "plan dtype %d does not match the entry point", p->dtype);
   DSP_CHECK(batch >= 0, "negative batch");
   if (batch == 0) return DSPB200_OK;
   DSP_CHECK(in != nullptr && out != nullptr, "NULL buffer");
   DSP_CHECK(in != out, "in-place complex transform is not supported");
   DSP_TRY(ensure_device());
+  DSP_TRY(check_plan_device(p->device, "fft"));
   FftArgs<T> a{};
   a.x = in; a.out = reinterpret_cast<C*>(out); a.n_frames = 1;
   const FftSide& s = p->c2c_side;
@@ -1371,7 +1374,7 @@ template int fftmag_run<float>(const dspb200_fft_plan*, const float*, int64_t, i
 template int fftmag_run<double>(const dspb200_fft_plan*, const double*, int64_t, int64_t, int64_t, int64_t, int64_t, double*, int64_t, int64_t, int64_t, void*, size_t, cudaStream_t);
 
 int fft_plan_info(const dspb200_fft_plan* plan, int* n_fft, int* dtype) {
-  if (!plan) return fail(DSPB200_ERR_INVALID, "fft plan is NULL");
+  DSP_PLAN(plan, kMagicFft, "fft");
   *n_fft = plan->n_fft; *dtype = plan->dtype;
   return DSPB200_OK;
 }
@@ -1380,7 +1383,7 @@ template <typename T>
 static int fftmag_host(const dspb200_fft_plan* p, const T* x, int64_t channels, int64_t n_samples, int64_t offset,
                        int64_t hop, int64_t n_frames, T* mag) {
   typedef typename Cpx<T>::type C;
-  DSP_CHECK(p != nullptr, "plan is NULL");
+  DSP_PLAN(p, kMagicFft, "fft");
   DSP_CHECK(channels >= 0 && n_samples >= 0 && n_frames >= 0, "negative shape");
   if (channels == 0 || n_frames == 0) return DSPB200_OK;
   DSP_CHECK(mag != nullptr && (x != nullptr || n_samples == 0), "NULL buffer");
@@ -1434,6 +1437,8 @@ int dspb200_fft_plan_create(int n_fft, int hann, int dtype, dspb200_fft_plan** p
 
 int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
   if (!p) return DSPB200_OK;
+  DSP_PLAN(p, kMagicFft, "fft");
+  p->magic = 0;
   cudaFree(p->d_fs_hi);
   cudaFree(p->d_fs_lo);
   FftSide* sides[4] = {&p->real_side, &p->c2c_side, &p->fs_cols, &p->fs_rows};
@@ -1451,7 +1456,8 @@ int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
 }
 
 int dspb200_fft_workspace_bytes(const dspb200_fft_plan* p, int64_t n_transforms, size_t* bytes) {
-  DSP_CHECK(p != nullptr && bytes != nullptr, "NULL argument");
+  DSP_PLAN(p, kMagicFft, "fft");
+  DSP_CHECK(bytes != nullptr, "NULL argument");
   DSP_CHECK(n_transforms >= 0, "negative transform count");
   const size_t csize = p->dtype == DSPB200_F32 ? 8 : 16;
   const size_t r = side_workspace(p->real_side, n_transforms, csize);
@@ -1474,26 +1480,31 @@ int dspb200_fftmag_run_f64(const dspb200_fft_plan* p, const double* x, int64_t x
 }
 int dspb200_fft_c2c_run_f32(const dspb200_fft_plan* p, const float* in, float* out, int64_t batch, void* ws,
                             size_t ws_bytes, void* stream) {
-  DSP_CHECK(p && p->c2c_side.nc > 0, "plan is NULL or too long for the complex transform");
+  DSP_PLAN(p, kMagicFft, "fft");
+  DSP_CHECK(p->c2c_side.nc > 0, "plan is too long for the complex transform");
   return fft_c2c_run<float>(p, in, out, batch, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int dspb200_fft_c2c_run_f64(const dspb200_fft_plan* p, const double* in, double* out, int64_t batch, void* ws,
                             size_t ws_bytes, void* stream) {
-  DSP_CHECK(p && p->c2c_side.nc > 0, "plan is NULL or too long for the complex transform");
+  DSP_PLAN(p, kMagicFft, "fft");
+  DSP_CHECK(p->c2c_side.nc > 0, "plan is too long for the complex transform");
   return fft_c2c_run<double>(p, in, out, batch, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int dspb200_fftmag_host_f32(const dspb200_fft_plan* p, const float* x, int64_t channels, int64_t n_samples,
                             int64_t offset, int64_t hop, int64_t n_frames, float* mag) {
-  DSP_CHECK(p && p->dtype == DSPB200_F32, "plan is NULL or not float32");
+  DSP_PLAN(p, kMagicFft, "fft");
+  DSP_CHECK(p->dtype == DSPB200_F32, "plan is not float32");
   return fftmag_host<float>(p, x, channels, n_samples, offset, hop, n_frames, mag);
 }
 int dspb200_fftmag_host_f64(const dspb200_fft_plan* p, const double* x, int64_t channels, int64_t n_samples,
                             int64_t offset, int64_t hop, int64_t n_frames, double* mag) {
-  DSP_CHECK(p && p->dtype == DSPB200_F64, "plan is NULL or not float64");
+  DSP_PLAN(p, kMagicFft, "fft");
+  DSP_CHECK(p->dtype == DSPB200_F64, "plan is not float64");
   return fftmag_host<double>(p, x, channels, n_samples, offset, hop, n_frames, mag);
 }
 int dspb200_fft_c2c_host_f64(const dspb200_fft_plan* p, const double* in, double* out, int64_t batch) {
-  DSP_CHECK(p && p->dtype == DSPB200_F64 && p->c2c_side.nc > 0, "plan is NULL, not float64 or too long");
+  DSP_PLAN(p, kMagicFft, "fft");
+  DSP_CHECK(p->dtype == DSPB200_F64 && p->c2c_side.nc > 0, "plan is not float64 or too long");
   DSP_CHECK(batch >= 0, "negative batch");
   if (batch == 0) return DSPB200_OK;
   DSP_CHECK(in != nullptr && out != nullptr, "NULL buffer");

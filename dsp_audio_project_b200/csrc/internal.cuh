@@ -51,7 +51,7 @@ struct LtiChunkSystem {
   int rows = 0, states = 0;
   std::vector<double> tk, o, phi;
 };
-int lti_chunk_system(const Section* sec, int ns, LtiChunkSystem& cs);
+int lti_chunk_system(const Section* sec, int ns, LtiChunkSystem& cs, int rows = 0);
 void cascade_state_space(const Section* sec, int ns, std::vector<double>& A, std::vector<double>& B,
                          std::vector<double>& C, double& D);
 int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp);
@@ -64,6 +64,34 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
                 int64_t n_in, int64_t n_out, bool clip, float* state, bool state_in, cudaStream_t stream);
 bool lti_mma_possible(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs);
 int lti_mma_chunk();
+// K1 + K2 fused on tcgen05 (xz_mma.cu): x -> z in one pass, y never touches HBM.  fp32 I/O, 160/147-shaped ratios.
+struct XzPlan {
+  int ok = 0;
+  int L = 0, M = 0, device = -1;
+  int states = 0;          // 2 * sections, padded to a multiple of 4
+  int tab_rows = 0;        // rows of 64 fp16 in d_table
+  uint32_t tab_bytes = 0, o_off = 0;
+  uint32_t blk_off[2][2][2] = {};
+  int blk_row0[2][2] = {};
+  int r0[2][8] = {};
+  int first_new = 0, start0 = 0;
+  float unscale = 0.f;
+  void* d_table = nullptr;   // [phase][hi, lo][block] coefficient tiles of G_ph = [T; K] A_ph, then the free-response operand
+  float phi[kLtiMaxStates * kLtiMaxStates] = {};
+};
+int xz_build(const std::vector<double>& taps, int L, int M, const Section* sec, int ns, XzPlan& xp);
+void xz_free(XzPlan& xp);
+int xz_chunk();
+bool xz_possible(const XzPlan& xp, const float* x, int64_t xs, const float* z, int64_t zs, int64_t n_in, int n_taps);
+bool xz_usable(const XzPlan& xp, const float* x, int64_t xs, const float* z, int64_t zs, int64_t channels, int64_t n_in,
+               int n_taps);
+int xz_run(const XzPlan& xp, const float* x, int64_t xs, float* z, int64_t zs, int64_t channels, int64_t n_in, int64_t n_out,
+           bool clip, cudaStream_t stream);
+// the fused tables of (src plan, eq plan), built on first use and cached in the eq plan; *xp is NULL when the pair has no
+// fused form (other ratios, more than 8 sections, float64)
+int eq_plan_xz(const dspb200_eq_plan* eq, const dspb200_src_plan* src, const XzPlan** xp);
+int eq_plan_clip(const dspb200_eq_plan* plan);
+const std::vector<double>* src_plan_taps(const dspb200_src_plan* plan);
 int fft_plan_info(const dspb200_fft_plan* plan, int* n_fft, int* dtype);
 int eq_plan_dtype(const dspb200_eq_plan* plan);
 }  // namespace dspb200

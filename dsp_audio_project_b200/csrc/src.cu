@@ -385,6 +385,7 @@ src_generic_kernel(const T* __restrict__ x, long long x_stride, T* __restrict__ 
 }  // namespace dspb200
 
 struct dspb200_src_plan {
+  uint32_t magic = dspb200::kMagicSrc;   // first member: checked by every entry point
   int L, M, dtype, n_taps;
   int device;
   std::vector<double> taps;   // h * L, float64
@@ -495,7 +496,7 @@ static void build_tiled(const std::vector<double>& h, int L, int M, int smem_lim
 template <typename T>
 int src_run(const dspb200_src_plan* plan, const T* x, int64_t xs, T* y, int64_t ys,
             int64_t channels, int64_t n_in, cudaStream_t stream, int force_kind) {
-  DSP_CHECK(plan != nullptr, "plan is NULL");
+  DSP_PLAN(plan, kMagicSrc, "src");
   DSP_CHECK(plan->dtype == DType<T>::id, "plan dtype %d does not match the entry point", plan->dtype);
   DSP_CHECK(channels >= 0, "negative channel count");
   DSP_CHECK(n_in >= 1, "input must hold at least one sample (numpy.convolve rejects empty input)");
@@ -503,6 +504,7 @@ int src_run(const dspb200_src_plan* plan, const T* x, int64_t xs, T* y, int64_t 
   if (channels == 0) return DSPB200_OK;
   DSP_CHECK(x != nullptr && y != nullptr, "NULL buffer");
   DSP_TRY(ensure_device());
+  DSP_TRY(check_plan_device(plan->device, "src"));
   int Tt; int64_t P, n_out;
   src_geometry(plan->L, plan->M, n_in, Tt, P, n_out);
   DSP_CHECK(xs >= n_in && ys >= n_out, "channel stride smaller than the row length");
@@ -572,9 +574,13 @@ template int src_run<float>(const dspb200_src_plan*, const float*, int64_t, floa
 template int src_run<double>(const dspb200_src_plan*, const double*, int64_t, double*, int64_t, int64_t, int64_t, cudaStream_t, int);
 
 int src_plan_ratio(const dspb200_src_plan* plan, int* L, int* M, int* dtype) {
-  if (!plan) return fail(DSPB200_ERR_INVALID, "src plan is NULL");
+  DSP_PLAN(plan, kMagicSrc, "src");
   *L = plan->L; *M = plan->M; *dtype = plan->dtype;
   return DSPB200_OK;
+}
+
+const std::vector<double>* src_plan_taps(const dspb200_src_plan* plan) {
+  return (plan && plan->magic == kMagicSrc) ? &plan->taps : nullptr;
 }
 
 template <typename T>
@@ -676,6 +682,8 @@ int dspb200_src_plan_create(int L, int M, int dtype, dspb200_src_plan** plan) {
 
 int dspb200_src_plan_destroy(dspb200_src_plan* p) {
   if (!p) return DSPB200_OK;
+  DSP_PLAN(p, kMagicSrc, "src");
+  p->magic = 0;
   cudaFree(p->d_taps);
   cudaFree(p->d_table);
   cudaFree(p->d_group_lo);
@@ -687,7 +695,8 @@ int dspb200_src_plan_destroy(dspb200_src_plan* p) {
 
 int dspb200_src_plan_kernel_kind(const dspb200_src_plan* plan, int64_t channels, int64_t n_in,
                                  int64_t x_stride, int* kind) {
-  DSP_CHECK(plan != nullptr && kind != nullptr, "NULL argument");
+  DSP_PLAN(plan, kMagicSrc, "src");
+  DSP_CHECK(kind != nullptr, "NULL argument");
   (void)channels; (void)x_stride;
   const int T = plan->n_taps;
   *kind = (plan->geom.ok && n_in * plan->L >= T) ? 1 : 0;

@@ -136,35 +136,6 @@ class SrcPlan:
                      _stream_ptr(x)))
         return out
 
-    def run_stream(self, x, state=None, out=None):
-        """One time block of a longer signal (float32): `state` is None for the first block, afterwards the
-        tensor this call returned for the previous block.  Blocks other than the last must be multiples of
-        `stream_chunk()` samples.  Returns (z, state)."""
-        torch = _torch()
-        _check_tensor(x, self.dtype_id, "x")
-        if self.dtype_id != F32:
-            raise ValueError("the streaming form is float32 only")
-        if out is None:
-            out = torch.empty_like(x)
-        _check_tensor(out, self.dtype_id, "out")
-        if out.shape != x.shape:
-            raise ValueError("out must have x's shape")
-        ch, n = x.shape
-        first = state is None
-        if first:
-            state = torch.zeros((ch, 16), dtype=torch.float32, device=x.device)
-        elif state.shape != (ch, 16) or state.dtype != torch.float32 or not state.is_contiguous() or state.device != x.device:
-            raise ValueError("state must be the [channels, 16] float32 tensor a previous run_stream returned")
-        with torch.cuda.device(x.device):
-            check(_lib.load().dspb200_eq_run_stream_f32(self._h, x.data_ptr(), _row_stride(x), out.data_ptr(),
-                                                        _row_stride(out), ch, n, state.data_ptr(), int(first),
-                                                        _stream_ptr(x)))
-        return out, state
-
-    @staticmethod
-    def stream_chunk() -> int:
-        return int(_lib.load().dspb200_eq_stream_chunk())
-
     def run_host(self, x):
         a = _as_host(x, self.dtype_id)
         ch, n_in = a.shape
@@ -421,16 +392,48 @@ class Chain:
     def out_len(self, n_in):
         return self.src.out_len(n_in) if self.src else n_in
 
-    def run(self, x, *, keep_y=False):
-        """x [channels, n_in] CUDA tensor -> (y or None, z, mag)."""
+    def kernel_kind(self, channels: int, n_in: int) -> str:
+        """"fused" when run() without keep_y would run SRC and EQ as the one tensor-core kernel that never writes y
+        (wide float32 batches of a 160/147-shaped ratio), else "cascade" (three kernels)."""
+        if self.src is None or self.eq is None or self.dtype_id != F32:
+            return "cascade"
+        k = C.c_int()
+        check(_lib.load().dspb200_chain_kernel_kind(self.src._h, self.eq._h, channels, n_in, -(-n_in // 4) * 4, C.byref(k)))
+        return "fused" if k.value == 1 else "cascade"
+
+    def run_fused(self, x, out=None):
+        """Test hook: SRC->EQ through the fused kernel at any batch width (float32).  x [channels, n_in] -> z."""
+        torch = _torch()
+        _check_tensor(x, self.dtype_id, "x")
+        if self.src is None or self.eq is None:
+            raise ValueError("the fused form needs both a resampler and an equaliser")
+        ch, n_in = x.shape
+        n_out = self.out_len(n_in)
+        if out is None:
+            pitch = -(-n_out // 4) * 4
+            out = torch.empty((ch, pitch), dtype=x.dtype, device=x.device)[:, :n_out]
+        _check_tensor(out, self.dtype_id, "out")
+        with torch.cuda.device(x.device):
+            check(_lib.load().dspb200_chain_fused_f32(self.src._h, self.eq._h, x.data_ptr(), _row_stride(x), ch, n_in,
+                                                      out.data_ptr(), _row_stride(out), _stream_ptr(x)))
+        return out
+
+    def run(self, x, *, keep_y=False, z=None, mag=None):
+        """x [channels, n_in] CUDA tensor -> (y or None, z, mag).  z / mag: optional preallocated contiguous outputs."""
         torch = _torch()
         _check_tensor(x, self.dtype_id, "x")
         ch, n_in = x.shape
         n_out = self.out_len(n_in)
         n_frames = n_out // self.fft.n_fft
-        z = torch.empty((ch, n_out), dtype=x.dtype, device=x.device)
+        if z is None:
+            z = torch.empty((ch, n_out), dtype=x.dtype, device=x.device)
+        elif tuple(z.shape) != (ch, n_out) or not z.is_contiguous() or z.dtype != x.dtype:
+            raise ValueError(f"z must be a contiguous [{ch}, {n_out}] tensor of x's dtype")
         y = torch.empty((ch, n_out), dtype=x.dtype, device=x.device) if (keep_y and self.src) else None
-        mag = torch.empty((ch, n_frames, self.fft.bins), dtype=x.dtype, device=x.device)
+        if mag is None:
+            mag = torch.empty((ch, n_frames, self.fft.bins), dtype=x.dtype, device=x.device)
+        elif tuple(mag.shape) != (ch, n_frames, self.fft.bins) or not mag.is_contiguous() or mag.dtype != x.dtype:
+            raise ValueError(f"mag must be a contiguous [{ch}, {n_frames}, {self.fft.bins}] tensor of x's dtype")
         need = C.c_size_t()
         lib = _lib.load()
         check(lib.dspb200_chain_workspace_bytes(self.src._h if self.src else None, self.fft._h, ch, n_in,

@@ -219,10 +219,16 @@ int dspb200_fft_c2c_host_f64(const dspb200_fft_plan* plan, const double* in, dou
 
 /* ---- the app's cascade SRC -> EQ -> framed spectra (app.py:161-167) ---- */
 /* Device form: x [channels, n_in] -> y [channels, n_out] (SRC output, may be
- * NULL when the caller does not keep it: a scratch of the same shape is then
- * taken from `workspace`), z [channels, n_out] (EQ output), mag
+ * NULL when the caller does not keep it), z [channels, n_out] (EQ output), mag
  * [channels, n_frames, n_fft/2+1] with non-overlapping frames (hop = n_fft,
- * tail dropped).  eq may be NULL (bypass: z = y). */
+ * tail dropped).  eq may be NULL (bypass: z = y).
+ * With y == NULL (what app.py:164-167 does: y is only ever the EQ's input) wide
+ * float32 batches of a 160/147-shaped ratio run SRC and EQ as ONE kernel that
+ * reads x once and writes z once (xz_mma.cu; DSPB200_CHAIN_NO_FUSED=1 in the
+ * environment disables it, DSPB200_CHAIN_FORCE_FUSED=1 uses it at any batch
+ * width); otherwise the resampler writes into z and the equaliser runs in
+ * place.  The fused form needs |x| < 1023 (fp16 operand pieces).
+ * `workspace` only serves long FFTs (dspb200_fft_workspace_bytes). */
 int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_fft_plan* fft,
                                   int64_t channels, int64_t n_in, int keep_y, size_t* bytes);
 int dspb200_chain_run_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq,
@@ -233,6 +239,10 @@ int dspb200_chain_run_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq
                           const dspb200_fft_plan* fft, const double* x, int64_t x_stride,
                           int64_t channels, int64_t n_in, double* y, double* z, double* mag,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* 1 in *kind when dspb200_chain_run_f32 with y == NULL would use the fused
+ * SRC->EQ kernel for this shape (16-byte aligned rows assumed), else 0. */
+int dspb200_chain_kernel_kind(const dspb200_src_plan* src, const dspb200_eq_plan* eq, int64_t channels,
+                              int64_t n_in, int64_t x_stride, int* kind);
 /* Host form: pinned or pageable host buffers in, host buffers out; copies are
  * pipelined against the kernels in channel slabs.  z and mag are dense. */
 int dspb200_chain_host_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq,
