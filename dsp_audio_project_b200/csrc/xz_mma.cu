@@ -34,6 +34,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "design.cuh"
@@ -48,14 +49,21 @@ constexpr int kTM = 128;            // channels per group (MMA M, TMEM lanes)
 constexpr int kC = 80;              // outputs per chunk
 constexpr int kND = 96;             // accumulator columns = coefficient rows: 80 outputs + 16 state slots
 constexpr int kNks = 8;             // k-steps of 16 window samples
-constexpr int kWin = 113;           // window samples per chunk (both phases of 160/147)
-constexpr int kNew0 = 73, kNew1 = 74;   // new samples of an even / odd chunk; the other 40 / 39 are carried in registers
+constexpr int kWin = 114;           // window samples per chunk: the 113 a chunk's FIR windows reach, plus one so that both phases
+                                    // have the same shape (40 carried + 74 new); the extra column of G_ph is zero
+constexpr int kNew = 74;            // samples read per chunk; consecutive windows start 73 (after an even chunk) or 74 apart
+constexpr int kAdv0 = 73, kAdv1 = 74;
 constexpr int kHalo = 40;
-constexpr int kXSlots = 7;
+constexpr int kXSlots = 6;
+constexpr int kStages = 2;            // staging tiles of the TMA stores
 constexpr uint32_t kBoxBytes = kTM * 32 * 4;   // [128 channels x 32 samples] fp32, 128-byte rows, swizzled
 constexpr int kEpiWarps = 4, kConvWarps = 4;
 constexpr int kConvWarp0 = 4, kTmaWarp = 8, kMmaWarp = 9;
-constexpr int kThreads = 10 * 32;
+constexpr int kThreads = 12 * 32;   // three warpgroups: epilogue, converters, {TMA, MMA, two idle warps}
+// registers are re-divided between the warpgroups at kernel start (setmaxnreg); the pool is what the launch allotted,
+// 384 threads x 168: the three counts must not add up to more than 3 x 168 = 504 or an increase waits for ever
+constexpr int kRegsEpi = 200, kRegsConv = 208, kRegsAux = 96;
+static_assert(kRegsEpi + kRegsConv + kRegsAux <= 3 * 168, "setmaxnreg budget");
 constexpr uint32_t kColX = 0;       // window buffers: [2][hi 64 | lo 64] columns
 constexpr uint32_t kColD = 256;     // accumulators: [2][96]
 constexpr uint32_t kColS = 448;     // split state [s1 | s2 | s3], 8 columns (16 fp16) each
@@ -72,6 +80,7 @@ struct XzArgs {
   uint32_t blk_off[2][2][2];    // [phase][hi, lo][64-sample block]: byte offset of the tile in the table
   int blk_row0[2][2];           // first coefficient row a tile holds
   int r0[2][kNks];              // first coefficient row the k-step's MMAs touch (multiple of 16)
+  unsigned long long* prof;     // development (DSPB200_XZ_PROF=1): cycles per phase of each role, CTA 0
   float phi[kLtiMaxStates * kLtiMaxStates];
 };
 
@@ -85,18 +94,28 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
 
+// (v0, v1) x scale -> packed fp16 hi and lo (round to nearest even): six instructions per pair with the packed fp32 forms
+__device__ __forceinline__ void split_pair(float v0, float v1, float scale, uint32_t& hi, uint32_t& lo) {
+  const float2 as = fmul2s(make_float2(v0, v1), scale);
+  hi = pack_h2(as.x, as.y);
+  const float2 d = ffma2s(unpack_h2(hi), -1.f, as);
+  lo = pack_h2(d.x, d.y);
+}
+
+// s <- Phi s + u.  phi_t is Phi transposed (phi_t[j][i] = Phi[i][j]) in the kernel parameters: a packed FFMA takes the
+// coefficient pair (Phi[2i][j], Phi[2i+1][j]) from the constant bank and s[j] as the broadcast operand.
 template <int kS>
-__device__ __forceinline__ void advance_state(float (&s)[kS], const float* __restrict__ phi, const float (&u)[kS]) {
-  float t[kS];
+__device__ __forceinline__ void advance_state(float (&s)[kS], const float* __restrict__ phi_t, const float (&u)[kS]) {
+  float2 t[kS / 2];
 #pragma unroll
-  for (int i = 0; i < kS; ++i) {
-    float acc = u[i];
+  for (int i = 0; i < kS / 2; ++i) t[i] = make_float2(u[2 * i], u[2 * i + 1]);
 #pragma unroll
-    for (int j = 0; j < kS; ++j) acc = fmaf(phi[i * kLtiMaxStates + j], s[j], acc);
-    t[i] = acc;
-  }
+  for (int j = 0; j < kS; ++j)
 #pragma unroll
-  for (int i = 0; i < kS; ++i) s[i] = t[i];
+    for (int i = 0; i < kS / 2; ++i)
+      ffma2_bcast(t[i], *reinterpret_cast<const float2*>(phi_t + j * kLtiMaxStates + 2 * i), s[j]);
+#pragma unroll
+  for (int i = 0; i < kS / 2; ++i) { s[2 * i] = t[i].x; s[2 * i + 1] = t[i].y; }
 }
 
 // The converter's view of the x ring: boxes are numbered from the group's first one; `base` is the running box count
@@ -160,16 +179,20 @@ __device__ __forceinline__ void release_upto(XRing& q, int next_pos, int lane) {
   if (upto > q.released) q.released = upto;
 }
 
-// One chunk of the converter: window = [carried halo | new samples]; split every sample x 2^6 into fp16 hi + lo and
-// store packed pairs to the window buffer in tensor memory (column c = samples 2c, 2c + 1).
-template <int PH>
-__device__ __forceinline__ void convert_chunk(float (&carry)[kHalo], int pos, XRing& q, int row, int lane, float x_scale,
-                                              uint32_t tbuf) {
-  constexpr int NEW = PH ? kNew1 : kNew0, H = kWin - NEW;
+// One chunk of the converter: window = [40 carried samples | 74 new samples]; split every sample x 2^6 into fp16 hi + lo and
+// store packed pairs to the window buffer in tensor memory (column c = samples 2c, 2c + 1).  The next window starts
+// `adv` = 73 or 74 samples on: its first 40 samples are kept in `carry`.  One code path for both phases: the kernel is
+// bound by instruction fetch before anything else.
+__device__ __forceinline__ void convert_chunk(float (&carry)[kHalo], int pos, int adv, XRing& q, int row, int lane, float x_scale,
+                                              uint32_t tbuf, unsigned long long* prof) {
   float r[80];
+  long long t0 = 0;
+  if (prof) t0 = clock64();
   read_run<20>(r, pos, q, row);
+  if (prof) atomicAdd(prof + 2, static_cast<unsigned long long>(clock64() - t0));   // box waits + shared-memory reads
+  release_upto(q, pos + adv, lane);     // the samples are in registers: hand the boxes behind the next chunk's start back now
   auto win = [&](int w) -> float {   // compile-time index after unrolling
-    return w < H ? carry[w + (kHalo - H)] : (w < kWin ? r[w - H] : 0.f);
+    return w < kHalo ? carry[w] : (w < kWin ? r[w - kHalo] : 0.f);
   };
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -178,10 +201,7 @@ __device__ __forceinline__ void convert_chunk(float (&carry)[kHalo], int pos, XR
     for (int c = 0; c < 16; ++c) {
       const int w = 32 * g + 2 * c;
       if (w < kWin) {
-        const float a0 = win(w) * x_scale, a1 = win(w + 1) * x_scale;
-        hi[c] = pack_h2(a0, a1);
-        const float2 hf = unpack_h2(hi[c]);
-        lo[c] = pack_h2(a0 - hf.x, a1 - hf.y);
+        split_pair(win(w), win(w + 1), x_scale, hi[c], lo[c]);
       } else {
         hi[c] = 0u;
         lo[c] = 0u;
@@ -190,9 +210,13 @@ __device__ __forceinline__ void convert_chunk(float (&carry)[kHalo], int pos, XR
     tmem_st16(tbuf + 16 * g, hi);
     tmem_st16(tbuf + 64 + 16 * g, lo);
   }
+  if (adv == kAdv1) {
 #pragma unroll
-  for (int j = 0; j < kHalo; ++j) carry[j] = r[NEW - kHalo + j];
-  release_upto(q, pos + NEW, lane);
+    for (int j = 0; j < kHalo; ++j) carry[j] = r[kAdv1 - kHalo + j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < kHalo; ++j) carry[j] = r[kAdv0 - kHalo + j];
+  }
 }
 
 template <int kS>
@@ -200,10 +224,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
               const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ XzArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];   // no static shared memory in this kernel: the window starts 1024-aligned
-  // layout: coefficient tiles | x ring | staging tile | barriers
+  // layout: coefficient tiles | x ring | staging tiles | barriers
   unsigned char* xring = smem + a.tab_bytes;
   unsigned char* stage = xring + kXSlots * kBoxBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + kBoxBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + kStages * kBoxBytes);
   uint64_t* full_x = bars;                    // [x slot] TMA landed the box
   uint64_t* empty_x = full_x + kXSlots;       // [x slot] all four converter warps are done with it
   uint64_t* x_ready = empty_x + kXSlots;      // [2] window buffer written to tensor memory
@@ -213,6 +237,7 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
   uint64_t* tab_full = acc_empty + 2;         // coefficient tiles resident
   uint64_t* s_ready = tab_full + 1;           // the next chunk's start states are in tensor memory
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(s_ready + 1);
+  uint4* mma_tab = reinterpret_cast<uint4*>(bars + 32);     // [2 phases][8 k-steps], written and read by the MMA thread
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -231,9 +256,18 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_base_s;
+  long long prof_c0 = 0;
+  unsigned long long prof_g0 = 0;
+  if (a.prof != nullptr && threadIdx.x == 0) {
+    prof_c0 = clock64();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(prof_g0));
+  }
   const int n_local = (a.n_groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
-  if (warp == kTmaWarp) {
+  if (warp >= 2 * 4) {
+   // third warpgroup (TMA producer, MMA issuer, two idle warps): gives most of its registers to the other two
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
+   if (warp == kTmaWarp) {
     // ---------------- TMA producer: coefficient tiles once, then the x boxes of each group in time order ----------------
     if (lane == 0) {
       tma_prefetch_desc(&tm_g);
@@ -252,48 +286,71 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+   } else if (warp == kMmaWarp) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
+      // loop invariants of the two phases -- accumulator column, instruction descriptor and the two coefficient descriptors
+      // of every k-step -- in shared memory, so that the issue loop stays a loop (instruction fetch is what binds this kernel)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int j = 0; j < kNks; ++j) {
+          const int r0 = a.r0[ph][j], blk = j >> 2;
+          const uint32_t rel = static_cast<uint32_t>(r0 - a.blk_row0[ph][blk]) * 128u;
+          mma_tab[ph * kNks + j] = make_uint4(static_cast<uint32_t>(r0), umma_idesc_f16(kND - r0),
+                                              static_cast<uint32_t>(umma_desc_sw128(smem + a.blk_off[ph][0][blk] + rel)) + 2 * (j & 3),
+                                              static_cast<uint32_t>(umma_desc_sw128(smem + a.blk_off[ph][1][blk] + rel)) + 2 * (j & 3));
+        }
+      const uint64_t desc_hi = umma_desc_sw128(smem) & 0xFFFFFFFF00000000ull;
+      const uint64_t od = umma_desc_sw128(smem + a.o_off);
+      const uint32_t ido = umma_idesc_f16(kC);      // the end-state columns take no free response
       mbar_wait(tab_full, 0);
       uint32_t kk = 0, n_corr = 0;
       for (int gi = 0; gi < n_local; ++gi) {
         for (int k = 0; k < a.n_chunks; ++k, ++kk) {
           const uint32_t buf = kk & 1;
-          const int ph = k & 1;
+          const bool prof = a.prof != nullptr && blockIdx.x == 0;
+          long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+          if (prof) t0 = clock64();
           mbar_wait(&x_ready[buf], (kk >> 1) & 1);
+          if (prof) t1 = clock64();
           if (kk >= 2) mbar_wait(&acc_empty[buf], ((kk >> 1) - 1) & 1);
           tc_fence_after();
+          if (prof) t2 = clock64();
           const uint32_t d = tmem + kColD + buf * kND;
           const uint32_t xh = tmem + kColX + buf * 128, xl = xh + 64;
-#pragma unroll
+          const uint4* tab = mma_tab + (k & 1) * kNks;
+#pragma unroll 1
           for (int j = 0; j < kNks; ++j) {
-            const int r0 = a.r0[ph][j], blk = j >> 2;
-            const uint32_t idn = umma_idesc_f16(kND - r0);
-            const uint32_t rel = static_cast<uint32_t>(r0 - a.blk_row0[ph][blk]) * 128u;
-            const uint64_t gh = umma_desc_sw128(smem + a.blk_off[ph][0][blk] + rel) + 2 * (j & 3);
-            const uint64_t gl = umma_desc_sw128(smem + a.blk_off[ph][1][blk] + rel) + 2 * (j & 3);
-            umma_f16_ts(d + r0, xh + 8 * j, gh, idn, j ? 1u : 0u);   // k-step 0 reaches every row: it overwrites the accumulator
-            umma_f16_ts(d + r0, xh + 8 * j, gl, idn, 1u);
-            umma_f16_ts(d + r0, xl + 8 * j, gh, idn, 1u);
+            const uint4 t = tab[j];
+            const uint64_t gh = desc_hi | t.z, gl = desc_hi | t.w;
+            umma_f16_ts(d + t.x, xh + 8 * j, gh, t.y, j ? 1u : 0u);   // k-step 0 reaches every row: it overwrites the accumulator
+            umma_f16_ts(d + t.x, xh + 8 * j, gl, t.y, 1u);
+            umma_f16_ts(d + t.x, xl + 8 * j, gh, t.y, 1u);
           }
           umma_commit(&x_free[buf]);
+          if (prof) t3 = clock64();
           if (k > 0) {
             // z += [s1 | s2 | s3 | s1] . [O_hi | O_hi | O_hi | O_lo]^T ; chunk 0 starts from a zero state (lfilter, dsp_core.py:214)
             mbar_wait(s_ready, n_corr & 1);
             ++n_corr;
             tc_fence_after();
-            const uint64_t od = umma_desc_sw128(smem + a.o_off);
-            const uint32_t ido = umma_idesc_f16(kC);      // the end-state columns take no free response
 #pragma unroll
             for (int p = 0; p < 4; ++p) umma_f16_ts(d, tmem + kColS + 8 * (p == 3 ? 0 : p), od + 2 * p, ido, 1u);
           }
           umma_commit(&acc_full[buf]);
+          if (prof) {
+            atomicAdd(a.prof + 9, static_cast<unsigned long long>(t1 - t0));    // waiting for the window
+            atomicAdd(a.prof + 10, static_cast<unsigned long long>(t2 - t1));   // waiting for the accumulator
+            atomicAdd(a.prof + 11, static_cast<unsigned long long>(t3 - t2));   // issuing the main products
+            atomicAdd(a.prof + 12, static_cast<unsigned long long>(clock64() - t3));   // state + free response
+            atomicAdd(a.prof + 13, 1ull);
+          }
         }
       }
     }
+   }
   } else if (warp >= kConvWarp0) {
     // ---------------- converters: thread = channel = TMEM lane ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConv));
     const int row = (warp - kConvWarp0) * 32 + lane;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp - kConvWarp0) * 32) << 16);
     XRing q;
@@ -316,22 +373,30 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
       int pos = a.first_new;
       for (int k = 0; k < a.n_chunks; ++k, ++kk) {
         const uint32_t buf = kk & 1;
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == kConvWarp0 * 32;
+        long long t0 = 0, t1 = 0;
+        if (prof) t0 = clock64();
         if (kk >= 2) {
           mbar_wait(&x_free[buf], ((kk >> 1) - 1) & 1);
           tc_fence_after();
         }
+        if (prof) t1 = clock64();
         const uint32_t tbuf = lane_base + kColX + buf * 128;
-        if (k & 1) {
-          convert_chunk<1>(carry, pos, q, row, lane, a.x_scale, tbuf);
-          pos += kNew1;
-        } else {
-          convert_chunk<0>(carry, pos, q, row, lane, a.x_scale, tbuf);
-          pos += kNew0;
-        }
+        const int adv = (k & 1) ? kAdv1 : kAdv0;
+        convert_chunk(carry, pos, adv, q, row, lane, a.x_scale, tbuf, prof ? a.prof : nullptr);
+        pos += adv;
+        long long t2 = 0;
+        if (prof) t2 = clock64();
         tmem_wait_st();
+        if (prof) atomicAdd(a.prof + 14, static_cast<unsigned long long>(clock64() - t2));   // tcgen05.wait::st
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&x_ready[buf]);
+        if (prof) {
+          atomicAdd(a.prof + 0, static_cast<unsigned long long>(t1 - t0));            // waiting for the window buffer
+          atomicAdd(a.prof + 1, static_cast<unsigned long long>(clock64() - t1));     // boxes, conversion, tensor-memory stores
+          atomicAdd(a.prof + 3, 1ull);
+        }
       }
       // hand the group's remaining boxes back so the producer can go on with the next group
       __syncwarp();
@@ -345,11 +410,12 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
     }
   } else {
     // ---------------- epilogue warps 0-3: thread = TMEM lane = channel ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const int r = warp * 32 + lane;
-    const uint32_t row_addr = smem_u32(stage) + static_cast<uint32_t>(r) * 128u;
+    const uint32_t row_addr0 = smem_u32(stage) + static_cast<uint32_t>(r) * 128u;
     const uint32_t rx = static_cast<uint32_t>(r & 7);
-    uint32_t kk = 0;
+    uint32_t kk = 0, n_box = 0;      // boxes stored so far: box n goes through staging tile n mod kStages
     // the start state of the coming chunk, x 2^6 and split in three fp16 pieces, to tensor memory
     auto hand_over = [&](const float (&s)[kS]) {
       uint32_t w[3][8];
@@ -373,8 +439,13 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
     };
     // pieces [p0, p1) of the chunk (16 bytes each) into the staging tile at piece position pp0..; the tile must be free
     auto wait_stage = [&]() {
-      if (threadIdx.x == 0) tma_store_wait_read0();
+      long long tw = 0;
+      const bool pw = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+      if (pw) tw = clock64();
+      if (threadIdx.x == 0)      // the store that last used the coming tile has read it
+        asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStages - 1) : "memory");
       epi_bar();
+      if (pw) atomicAdd(a.prof + 16, static_cast<unsigned long long>(clock64() - tw));
     };
     for (int gi = 0; gi < n_local; ++gi) {
       const int g = static_cast<int>(blockIdx.x) + gi * static_cast<int>(gridDim.x);
@@ -383,8 +454,12 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
       for (int i = 0; i < kS; ++i) s[i] = 0.f;
       for (int k = 0; k < a.n_chunks; ++k, ++kk) {
         const uint32_t buf = kk & 1;
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        if (prof) t0 = clock64();
         mbar_wait(&acc_full[buf], (kk >> 1) & 1);
         tc_fence_after();
+        if (prof) t1 = clock64();
         const uint32_t taddr = lane_base + kColD + buf * kND;
         uint32_t v[6][16];
         tmem_ld16(v[5], taddr + kC);
@@ -394,6 +469,7 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (prof) t2 = clock64();
         // the next chunk's start state first: the MMA warp is waiting for it
         {
           float u[kS];
@@ -401,57 +477,75 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
           for (int i = 0; i < kS; ++i) u[i] = __uint_as_float(v[5][i]) * a.unscale;
           advance_state<kS>(s, a.phi, u);
         }
+        long long t2b = 0;
+        if (prof) t2b = clock64();
         if (k + 1 < a.n_chunks) hand_over(s);
+        if (prof) t3 = clock64();
+        if (prof) atomicAdd(a.prof + 15, static_cast<unsigned long long>(t3 - t2b));   // of "state": the hand-over
         // unscale, clip, stage, store.  Two chunks = 160 outputs = five boxes of 32: an even chunk fills boxes 0, 1 and the
         // first half of box 2 of its pair, the odd chunk the rest.
-        auto put = [&](int p, int pp) {   // piece p of the chunk (outputs 4p .. 4p+3) to piece position pp of the staging row
+        auto put = [&](int p, uint32_t pp) {   // piece p of the chunk (outputs 4p .. 4p+3) to piece position pp of the staging row
           float o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            o[e] = __uint_as_float(v[p >> 2][(p & 3) * 4 + e]) * a.unscale;
-            if (a.clip) o[e] = clip_unit(o[e]);
+          for (int e = 0; e < 4; e += 2) {
+            const float2 m = fmul2s(make_float2(__uint_as_float(v[p >> 2][(p & 3) * 4 + e]), __uint_as_float(v[p >> 2][(p & 3) * 4 + e + 1])),
+                                    a.unscale);
+            o[e] = m.x;
+            o[e + 1] = m.y;
+          }
+          if (a.clip) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = clip_unit(o[e]);
           }
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                       ::"r"(row_addr + ((static_cast<uint32_t>(pp) ^ rx) << 4)), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+                       ::"r"(row_addr0 + (n_box % kStages) * kBoxBytes + ((pp ^ rx) << 4)), "f"(o[0]), "f"(o[1]),
+                         "f"(o[2]), "f"(o[3]) : "memory");
         };
         auto send = [&](int box) {
           fence_proxy_async();
           epi_bar();
           if (threadIdx.x == 0) {
-            tma_store_2d(&tm_z, stage, box * 32, g * kTM);
+            tma_store_2d(&tm_z, stage + (n_box % kStages) * kBoxBytes, box * 32, g * kTM);
             tma_store_commit();
           }
+          ++n_box;
         };
-        const int box = 5 * (k >> 1);
-        if ((k & 1) == 0) {
-          wait_stage();
+        // staging position of the chunk's first piece and the pieces at which a box starts / is complete
+        const uint32_t off = (k & 1) ? 4u : 0u;
+        const uint32_t start_mask = (k & 1) ? 0x01010u : 0x10101u;           // odd: pieces 4, 12; even: 0, 8, 16
+        const uint32_t end_mask = (k & 1) ? 0x80808u : (k + 1 == a.n_chunks ? 0x88080u : 0x08080u);   // even: 7, 15 (+ 19 when the signal ends here: the hardware clips the rest)
+        int box = 5 * (k >> 1) + ((k & 1) ? 2 : 0);
 #pragma unroll
-          for (int p = 0; p < 8; ++p) put(p, p);
-          send(box);
-          wait_stage();
-#pragma unroll
-          for (int p = 8; p < 16; ++p) put(p, p - 8);
-          send(box + 1);
-          wait_stage();
-#pragma unroll
-          for (int p = 16; p < 20; ++p) put(p, p - 16);
-          if (k + 1 == a.n_chunks) send(box + 2);   // the signal ends inside this box: the hardware clips the rest
-        } else {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) put(p, p + 4);
-          send(box + 2);
-          wait_stage();
-#pragma unroll
-          for (int p = 4; p < 12; ++p) put(p, p - 4);
-          send(box + 3);
-          wait_stage();
-#pragma unroll
-          for (int p = 12; p < 20; ++p) put(p, p - 12);
-          send(box + 4);
+        for (int p = 0; p < 20; ++p) {
+          if ((p & 3) == 0 && ((start_mask >> p) & 1u)) wait_stage();
+          put(p, (static_cast<uint32_t>(p) + off) & 7u);
+          if ((p & 3) == 3 && ((end_mask >> p) & 1u)) send(box++);
+        }
+        if (prof) {
+          atomicAdd(a.prof + 4, static_cast<unsigned long long>(t1 - t0));           // waiting for the accumulator
+          atomicAdd(a.prof + 5, static_cast<unsigned long long>(t2 - t1));           // tensor memory -> registers
+          atomicAdd(a.prof + 6, static_cast<unsigned long long>(t3 - t2));           // state update + hand-over
+          atomicAdd(a.prof + 7, static_cast<unsigned long long>(clock64() - t3));    // clip + staging + stores
+          atomicAdd(a.prof + 8, 1ull);
         }
       }
     }
     if (threadIdx.x == 0) tma_store_wait_all0();
+    if (a.prof != nullptr && threadIdx.x == 0) {
+      unsigned long long g1;
+      unsigned smid;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      if (blockIdx.x == 0) {
+        a.prof[20] = static_cast<unsigned long long>(clock64() - prof_c0);
+        a.prof[21] = g1 - prof_g0;
+      }
+      if (blockIdx.x < 160) {      // per CTA: start and end time (ns), SM
+        a.prof[32 + 3 * blockIdx.x] = prof_g0;
+        a.prof[33 + 3 * blockIdx.x] = g1;
+        a.prof[34 + 3 * blockIdx.x] = smid;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -461,7 +555,7 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
 long long floor_div(long long x, long long y) { return x >= 0 ? x / y : -((-x + y - 1) / y); }
 
 size_t xz_smem_bytes(const XzPlan& xp) {
-  return static_cast<size_t>(xp.tab_bytes) + (kXSlots + 1) * static_cast<size_t>(kBoxBytes) + 32 * sizeof(uint64_t);
+  return static_cast<size_t>(xp.tab_bytes) + (kXSlots + kStages) * static_cast<size_t>(kBoxBytes) + 32 * sizeof(uint64_t) + 2 * kNks * sizeof(uint4);
 }
 
 template <int kS>
@@ -481,15 +575,17 @@ int xz_build(const std::vector<double>& taps, int L, int M, const Section* sec, 
   if (ns < 1 || 2 * ns > kLtiMaxStates) return DSPB200_OK;
   const long long T = static_cast<long long>(taps.size()), P = (T - 1) / 2;
   if ((static_cast<long long>(2 * kC) * M) % L != 0 || (static_cast<long long>(kC) * M) % L == 0) return DSPB200_OK;   // two phases
-  long long start[2], end[2];
+  // windows of the two phases: the 113 samples a chunk's FIR windows reach, widened to 114 so that both phases are
+  // [40 carried | 74 new]: an even chunk gets one sample more at the end, an odd chunk one at the start (zero columns of G)
+  long long start[2];
   for (int ph = 0; ph < 2; ++ph) {
     const long long m0 = static_cast<long long>(ph) * kC;
-    start[ph] = -floor_div(-(m0 * M + P - T + 1), L);
-    end[ph] = floor_div((m0 + kC - 1) * M + P, L);
-    if (end[ph] - start[ph] + 1 != kWin) return DSPB200_OK;
+    const long long first = -floor_div(-(m0 * M + P - T + 1), L), last = floor_div((m0 + kC - 1) * M + P, L);
+    if (last - first + 1 != kWin - 1) return DSPB200_OK;
+    start[ph] = first - ph;
   }
   const long long adv = static_cast<long long>(2 * kC) * M / L;
-  if (end[1] - end[0] != kNew1 || end[0] + adv - end[1] != kNew0) return DSPB200_OK;
+  if (start[1] - start[0] != kAdv0 || start[0] + adv - start[1] != kAdv1) return DSPB200_OK;
   LtiChunkSystem cs;
   DSP_TRY(lti_chunk_system(sec, ns, cs, kC));
   if (cs.rows != kC) return DSPB200_OK;
@@ -640,7 +736,7 @@ int xz_run(const XzPlan& xp, const float* x, int64_t xs, float* z, int64_t zs, i
   a.box0 = static_cast<int>(floor_div(floor_div(first_read, 4) * 4, 32));
   // last sample any chunk's aligned reads touch: start of its new range rounded down to 4, plus 80
   long long pos_last = xp.first_new;
-  for (int k = 0; k + 1 < a.n_chunks; ++k) pos_last += (k & 1) ? kNew1 : kNew0;
+  for (int k = 0; k + 1 < a.n_chunks; ++k) pos_last += (k & 1) ? kAdv1 : kAdv0;
   const long long last_read = floor_div(pos_last, 4) * 4 + 79;
   a.n_boxes = static_cast<int>(floor_div(last_read, 32) - a.box0 + 1);
   a.clip = clip ? 1 : 0;
@@ -652,17 +748,49 @@ int xz_run(const XzPlan& xp, const float* x, int64_t xs, float* z, int64_t zs, i
   memcpy(a.blk_off, xp.blk_off, sizeof(a.blk_off));
   memcpy(a.blk_row0, xp.blk_row0, sizeof(a.blk_row0));
   memcpy(a.r0, xp.r0, sizeof(a.r0));
-  memcpy(a.phi, xp.phi, sizeof(a.phi));
+  for (int i = 0; i < kLtiMaxStates; ++i)
+    for (int j = 0; j < kLtiMaxStates; ++j) a.phi[j * kLtiMaxStates + i] = xp.phi[i * kLtiMaxStates + j];   // transposed: see advance_state
   const int64_t sms = sm_count();
   const int grid = static_cast<int>(a.n_groups < sms ? a.n_groups : sms);
   const size_t smem = xz_smem_bytes(xp);
-  switch (xp.states) {
-    case 4: return launch<4>(tm_g, tm_x, tm_z, a, smem, grid, stream);
-    case 8: return launch<8>(tm_g, tm_x, tm_z, a, smem, grid, stream);
-    case 12: return launch<12>(tm_g, tm_x, tm_z, a, smem, grid, stream);
-    case 16: return launch<16>(tm_g, tm_x, tm_z, a, smem, grid, stream);
-    default: return fail(DSPB200_ERR_INVALID, "internal: bad state count %d", xp.states);
+  unsigned long long* prof = nullptr;
+  if (getenv("DSPB200_XZ_PROF") != nullptr) {
+    cudaMalloc(reinterpret_cast<void**>(&prof), 512 * sizeof(unsigned long long));
+    cudaMemset(prof, 0, 512 * sizeof(unsigned long long));
   }
+  a.prof = prof;
+  int rc;
+  switch (xp.states) {
+    case 4: rc = launch<4>(tm_g, tm_x, tm_z, a, smem, grid, stream); break;
+    case 8: rc = launch<8>(tm_g, tm_x, tm_z, a, smem, grid, stream); break;
+    case 12: rc = launch<12>(tm_g, tm_x, tm_z, a, smem, grid, stream); break;
+    case 16: rc = launch<16>(tm_g, tm_x, tm_z, a, smem, grid, stream); break;
+    default: rc = fail(DSPB200_ERR_INVALID, "internal: bad state count %d", xp.states);
+  }
+  if (prof) {
+    unsigned long long h[512];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(prof);
+    const double nc = h[3] ? static_cast<double>(h[3]) : 1.0, ne = h[8] ? static_cast<double>(h[8]) : 1.0,
+                 nm = h[13] ? static_cast<double>(h[13]) : 1.0;
+    fprintf(stderr,
+            "xz_mma: %d CTAs x %d chunks; cycles per chunk (CTA 0) -- converter: window buffer wait %.0f, boxes + conversion %.0f "
+            "(box waits + reads %.0f, wait::st %.0f); "
+            "epilogue: accumulator wait %.0f, tensor memory -> registers %.0f, state %.0f (hand-over %.0f), stores %.0f (tile waits %.0f); "
+            "mma: window wait %.0f, accumulator wait %.0f, main issue %.0f, state + free response %.0f; "
+            "CTA 0 ran %.3f ms at %.0f MHz\n",
+            grid, a.n_chunks, h[0] / nc, h[1] / nc, h[2] / nc, h[14] / nc, h[4] / ne, h[5] / ne, h[6] / ne, h[15] / ne, h[7] / ne,
+            h[16] / ne, h[9] / nm, h[10] / nm, h[11] / nm,
+            h[12] / nm, h[21] * 1e-6, h[21] ? h[20] * 1e3 / static_cast<double>(h[21]) : 0.0);
+    unsigned long long t_first = ~0ull;
+    for (int c = 0; c < grid && c < 160; ++c) t_first = h[32 + 3 * c] < t_first ? h[32 + 3 * c] : t_first;
+    fprintf(stderr, "xz_mma per CTA [cta: sm start end] ms:");
+    for (int c = 0; c < grid && c < 160; ++c)
+      fprintf(stderr, " [%d: %llu %.2f %.2f]", c, h[34 + 3 * c], (h[32 + 3 * c] - t_first) * 1e-6, (h[33 + 3 * c] - t_first) * 1e-6);
+    fprintf(stderr, "\n");
+  }
+  return rc;
 }
 
 }  // namespace dspb200
