@@ -54,7 +54,8 @@ constexpr int kWin = 114;           // window samples per chunk: the 113 a chunk
 constexpr int kNew = 74;            // samples read per chunk; consecutive windows start 73 (after an even chunk) or 74 apart
 constexpr int kAdv0 = 73, kAdv1 = 74;
 constexpr int kHalo = 40;
-constexpr int kXSlots = 6;
+constexpr int kXSlots = 6;             // x boxes in shared memory (the converter holds up to four); further ahead the boxes are
+constexpr int kPrefetch = 0;            // prefetched into L2, so a landing only has to cover the L2 latency
 constexpr int kStages = 2;            // staging tiles of the TMA stores
 constexpr uint32_t kBoxBytes = kTM * 32 * 4;   // [128 channels x 32 samples] fp32, 128-byte rows, swizzled
 constexpr int kEpiWarps = 4, kConvWarps = 4;
@@ -66,8 +67,13 @@ constexpr int kRegsEpi = 200, kRegsConv = 208, kRegsAux = 96;
 static_assert(kRegsEpi + kRegsConv + kRegsAux <= 3 * 168, "setmaxnreg budget");
 constexpr uint32_t kColX = 0;       // window buffers: [2][hi 64 | lo 64] columns
 constexpr uint32_t kColD = 256;     // accumulators: [2][96]
-constexpr uint32_t kColS = 448;     // split state [s1 | s2 | s3], 8 columns (16 fp16) each
+constexpr uint32_t kColS = 448;     // split state pieces, 32 columns: [s1 | s2 | s3 | s1 | s2] kS fp16 each (kS <= 12), else [s1 | s2 | s3] x 16
 constexpr int kXScaleExp = 6, kSScaleExp = 6;
+// Advance the state inside the free-response MMAs (rows 80.. of that operand hold Phi, five fp16 pieces of the state)?
+// Correct and 350 cycles per chunk shorter in the epilogue, but the 16 extra coefficient rows (2 KB) do not fit next to six
+// x boxes and two staging tiles, and giving up either costs more than it gains (5 boxes: 16.9 ms, one staging tile:
+// 16.7 ms against 12.7 ms per 18944-clip wave).  Kept for a cascade of at most 12 states should the budget change.
+constexpr bool kUseStateMma = false;
 
 struct XzArgs {
   long long channels, n_in, n_out;
@@ -84,7 +90,6 @@ struct XzArgs {
   float phi[kLtiMaxStates * kLtiMaxStates];
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {   // two fp16 (round to nearest even), `lo` in the low half
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -219,12 +224,20 @@ __device__ __forceinline__ void convert_chunk(float (&carry)[kHalo], int pos, in
   }
 }
 
-template <int kS>
+__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
+// kProf: the development instantiation (DSPB200_XZ_PROF=1) counts cycles per phase of each role; in the production one
+// `prof_p` is a compile-time NULL and every profiling branch leaves the binary (the kernel is bound by instruction fetch).
+template <int kS, bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
               const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ XzArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];   // no static shared memory in this kernel: the window starts 1024-aligned
-  // layout: coefficient tiles | x ring | staging tiles | barriers
+  // layout: coefficient tiles | x ring | staging tiles | barriers | MMA parameter table
   unsigned char* xring = smem + a.tab_bytes;
   unsigned char* stage = xring + kXSlots * kBoxBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage + kStages * kBoxBytes);
@@ -237,8 +250,10 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
   uint64_t* tab_full = acc_empty + 2;         // coefficient tiles resident
   uint64_t* s_ready = tab_full + 1;           // the next chunk's start states are in tensor memory
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(s_ready + 1);
-  uint4* mma_tab = reinterpret_cast<uint4*>(bars + 32);     // [2 phases][8 k-steps], written and read by the MMA thread
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4* mma_tab = reinterpret_cast<uint4*>(bars + 32);     // [2 phases][8 k-steps]
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
+  const int lane = threadIdx.x & 31;
+  unsigned long long* const prof_p = kProf ? a.prof : nullptr;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) __trap();   // the swizzle atoms need the 1024-byte alignment
@@ -258,92 +273,115 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
   const uint32_t tmem = *tmem_base_s;
   long long prof_c0 = 0;
   unsigned long long prof_g0 = 0;
-  if (a.prof != nullptr && threadIdx.x == 0) {
+  if (prof_p != nullptr && threadIdx.x == 0) {
     prof_c0 = clock64();
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(prof_g0));
   }
   const int n_local = (a.n_groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp >= 2 * 4) {
-   // third warpgroup (TMA producer, MMA issuer, two idle warps): gives most of its registers to the other two
+   // third warpgroup (TMA producer, MMA issuer, two idle warps): gives most of its registers to the other two.  Both roles
+   // run as whole converged warps and elect one lane per instruction: tcgen05 / TMA instructions issued from a divergent
+   // `lane == 0` region cost a seven-instruction election loop each.
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
    if (warp == kTmaWarp) {
     // ---------------- TMA producer: coefficient tiles once, then the x boxes of each group in time order ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tm_g);
       tma_prefetch_desc(&tm_x);
       mbar_expect_tx(tab_full, a.tab_bytes);
       for (uint32_t off = 0; off < a.tab_bytes; off += 16 * 128)      // boxes of 16 rows x 64 fp16
         tma_load_2d(smem + off, &tm_g, 0, static_cast<int>(off / 128), tab_full);
-      uint32_t it = 0;
-      for (int gi = 0; gi < n_local; ++gi) {
-        const int g = static_cast<int>(blockIdx.x) + gi * static_cast<int>(gridDim.x);
-        for (int bi = 0; bi < a.n_boxes; ++bi, ++it) {
-          const uint32_t s = it % kXSlots;
-          if (it >= kXSlots) mbar_wait(&empty_x[s], ((it / kXSlots) - 1) & 1);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int gi = 0; gi < n_local; ++gi) {
+      const int g = static_cast<int>(blockIdx.x) + gi * static_cast<int>(gridDim.x);
+      if (elect_one())
+        for (int bi = 0; bi < kPrefetch && bi < a.n_boxes; ++bi) tma_prefetch_l2_2d(&tm_x, (a.box0 + bi) * 32, g * kTM);
+      __syncwarp();
+      for (int bi = 0; bi < a.n_boxes; ++bi, ++it) {
+        const uint32_t s = it % kXSlots;
+        if (it >= kXSlots) mbar_wait(&empty_x[s], ((it / kXSlots) - 1) & 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_x[s], kBoxBytes);
           tma_load_2d(xring + s * kBoxBytes, &tm_x, (a.box0 + bi) * 32, g * kTM, &full_x[s]);
+          if (kPrefetch > 0 && bi + kPrefetch < a.n_boxes) tma_prefetch_l2_2d(&tm_x, (a.box0 + bi + kPrefetch) * 32, g * kTM);
         }
+        __syncwarp();
       }
     }
    } else if (warp == kMmaWarp) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      // loop invariants of the two phases -- accumulator column, instruction descriptor and the two coefficient descriptors
-      // of every k-step -- in shared memory, so that the issue loop stays a loop (instruction fetch is what binds this kernel)
-      for (int ph = 0; ph < 2; ++ph)
-        for (int j = 0; j < kNks; ++j) {
-          const int r0 = a.r0[ph][j], blk = j >> 2;
-          const uint32_t rel = static_cast<uint32_t>(r0 - a.blk_row0[ph][blk]) * 128u;
-          mma_tab[ph * kNks + j] = make_uint4(static_cast<uint32_t>(r0), umma_idesc_f16(kND - r0),
-                                              static_cast<uint32_t>(umma_desc_sw128(smem + a.blk_off[ph][0][blk] + rel)) + 2 * (j & 3),
-                                              static_cast<uint32_t>(umma_desc_sw128(smem + a.blk_off[ph][1][blk] + rel)) + 2 * (j & 3));
-        }
-      const uint64_t desc_hi = umma_desc_sw128(smem) & 0xFFFFFFFF00000000ull;
-      const uint64_t od = umma_desc_sw128(smem + a.o_off);
-      const uint32_t ido = umma_idesc_f16(kC);      // the end-state columns take no free response
-      mbar_wait(tab_full, 0);
-      uint32_t kk = 0, n_corr = 0;
-      for (int gi = 0; gi < n_local; ++gi) {
-        for (int k = 0; k < a.n_chunks; ++k, ++kk) {
-          const uint32_t buf = kk & 1;
-          const bool prof = a.prof != nullptr && blockIdx.x == 0;
-          long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-          if (prof) t0 = clock64();
-          mbar_wait(&x_ready[buf], (kk >> 1) & 1);
-          if (prof) t1 = clock64();
-          if (kk >= 2) mbar_wait(&acc_empty[buf], ((kk >> 1) - 1) & 1);
-          tc_fence_after();
-          if (prof) t2 = clock64();
-          const uint32_t d = tmem + kColD + buf * kND;
-          const uint32_t xh = tmem + kColX + buf * 128, xl = xh + 64;
-          const uint4* tab = mma_tab + (k & 1) * kNks;
+    // loop invariants of the two phases -- accumulator column, instruction descriptor and the two coefficient descriptors
+    // of every k-step -- in shared memory, so that the issue loop stays a loop
+    if (lane < 2 * kNks) {
+      const int ph = lane / kNks, j = lane % kNks;
+      const int r0 = a.r0[ph][j], blk = j >> 2;
+      const uint32_t rel = static_cast<uint32_t>(r0 - a.blk_row0[ph][blk]) * 128u;
+      mma_tab[lane] = make_uint4(static_cast<uint32_t>(r0), umma_idesc_f16(kND - r0),
+                                 static_cast<uint32_t>(umma_desc_sw128(smem + a.blk_off[ph][0][blk] + rel)) + 2 * (j & 3),
+                                 static_cast<uint32_t>(umma_desc_sw128(smem + a.blk_off[ph][1][blk] + rel)) + 2 * (j & 3));
+    }
+    __syncwarp();
+    const uint64_t desc_hi = umma_desc_sw128(smem) & 0xFFFFFFFF00000000ull;
+    const uint64_t od = umma_desc_sw128(smem + a.o_off);
+    // the free response of the start state; with 5 kS <= 64 the same four MMAs also advance the state (rows 80.. of the
+    // operand hold Phi): the accumulator's state columns then hold s' = Phi s + K x and nothing of the recurrence is left
+    // on the FMA pipe.  Wider cascades keep the state update in the epilogue and the state columns take no free response.
+    constexpr bool kStateMma = kUseStateMma && 5 * kS <= 64;
+    const uint32_t ido = umma_idesc_f16(kStateMma ? kND : kC);
+    mbar_wait(tab_full, 0);
+    uint32_t kk = 0, n_corr = 0;
+    for (int gi = 0; gi < n_local; ++gi) {
+      for (int k = 0; k < a.n_chunks; ++k, ++kk) {
+        const uint32_t buf = kk & 1;
+        const bool prof = prof_p != nullptr && blockIdx.x == 0 && lane == 0;
+        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        if (prof) t0 = clock64();
+        mbar_wait(&x_ready[buf], (kk >> 1) & 1);
+        if (prof) t1 = clock64();
+        if (kk >= 2) mbar_wait(&acc_empty[buf], ((kk >> 1) - 1) & 1);
+        tc_fence_after();
+        if (prof) t2 = clock64();
+        const uint32_t d = tmem + kColD + buf * kND;
+        const uint32_t xh = tmem + kColX + buf * 128, xl = xh + 64;
+        const uint4* tab = mma_tab + (k & 1) * kNks;
 #pragma unroll 1
-          for (int j = 0; j < kNks; ++j) {
-            const uint4 t = tab[j];
-            const uint64_t gh = desc_hi | t.z, gl = desc_hi | t.w;
+        for (int j = 0; j < kNks; ++j) {
+          const uint4 t = tab[j];
+          const uint64_t gh = desc_hi | t.z, gl = desc_hi | t.w;
+          if (elect_one()) {
             umma_f16_ts(d + t.x, xh + 8 * j, gh, t.y, j ? 1u : 0u);   // k-step 0 reaches every row: it overwrites the accumulator
             umma_f16_ts(d + t.x, xh + 8 * j, gl, t.y, 1u);
             umma_f16_ts(d + t.x, xl + 8 * j, gh, t.y, 1u);
           }
-          umma_commit(&x_free[buf]);
-          if (prof) t3 = clock64();
-          if (k > 0) {
-            // z += [s1 | s2 | s3 | s1] . [O_hi | O_hi | O_hi | O_lo]^T ; chunk 0 starts from a zero state (lfilter, dsp_core.py:214)
-            mbar_wait(s_ready, n_corr & 1);
-            ++n_corr;
-            tc_fence_after();
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(&x_free[buf]);
+        __syncwarp();
+        if (prof) t3 = clock64();
+        if (k > 0) {
+          // [z; s'] += [s1 | s2 | s3 | s1 | s2] . [O'_hi | O'_hi | O'_hi | O'_lo | O'_lo]^T (kS <= 12; else four pieces, O only);
+          // chunk 0 starts from a zero state (lfilter, dsp_core.py:214)
+          mbar_wait(s_ready, n_corr & 1);
+          ++n_corr;
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p) umma_f16_ts(d, tmem + kColS + 8 * (p == 3 ? 0 : p), od + 2 * p, ido, 1u);
+            for (int p = 0; p < 4; ++p)
+              umma_f16_ts(d, tmem + kColS + 8 * ((!kStateMma && p == 3) ? 0 : p), od + 2 * p, ido, 1u);
           }
-          umma_commit(&acc_full[buf]);
-          if (prof) {
-            atomicAdd(a.prof + 9, static_cast<unsigned long long>(t1 - t0));    // waiting for the window
-            atomicAdd(a.prof + 10, static_cast<unsigned long long>(t2 - t1));   // waiting for the accumulator
-            atomicAdd(a.prof + 11, static_cast<unsigned long long>(t3 - t2));   // issuing the main products
-            atomicAdd(a.prof + 12, static_cast<unsigned long long>(clock64() - t3));   // state + free response
-            atomicAdd(a.prof + 13, 1ull);
-          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
+        if (prof) {
+          atomicAdd(prof_p + 9, static_cast<unsigned long long>(t1 - t0));    // waiting for the window
+          atomicAdd(prof_p + 10, static_cast<unsigned long long>(t2 - t1));   // waiting for the accumulator
+          atomicAdd(prof_p + 11, static_cast<unsigned long long>(t3 - t2));   // issuing the main products
+          atomicAdd(prof_p + 12, static_cast<unsigned long long>(clock64() - t3));   // state + free response
+          atomicAdd(prof_p + 13, 1ull);
         }
       }
     }
@@ -373,7 +411,7 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
       int pos = a.first_new;
       for (int k = 0; k < a.n_chunks; ++k, ++kk) {
         const uint32_t buf = kk & 1;
-        const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == kConvWarp0 * 32;
+        const bool prof = prof_p != nullptr && blockIdx.x == 0 && threadIdx.x == kConvWarp0 * 32;
         long long t0 = 0, t1 = 0;
         if (prof) t0 = clock64();
         if (kk >= 2) {
@@ -383,19 +421,19 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
         if (prof) t1 = clock64();
         const uint32_t tbuf = lane_base + kColX + buf * 128;
         const int adv = (k & 1) ? kAdv1 : kAdv0;
-        convert_chunk(carry, pos, adv, q, row, lane, a.x_scale, tbuf, prof ? a.prof : nullptr);
+        convert_chunk(carry, pos, adv, q, row, lane, a.x_scale, tbuf, prof ? prof_p : nullptr);
         pos += adv;
         long long t2 = 0;
         if (prof) t2 = clock64();
         tmem_wait_st();
-        if (prof) atomicAdd(a.prof + 14, static_cast<unsigned long long>(clock64() - t2));   // tcgen05.wait::st
+        if (prof) atomicAdd(prof_p + 14, static_cast<unsigned long long>(clock64() - t2));   // tcgen05.wait::st
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&x_ready[buf]);
         if (prof) {
-          atomicAdd(a.prof + 0, static_cast<unsigned long long>(t1 - t0));            // waiting for the window buffer
-          atomicAdd(a.prof + 1, static_cast<unsigned long long>(clock64() - t1));     // boxes, conversion, tensor-memory stores
-          atomicAdd(a.prof + 3, 1ull);
+          atomicAdd(prof_p + 0, static_cast<unsigned long long>(t1 - t0));            // waiting for the window buffer
+          atomicAdd(prof_p + 1, static_cast<unsigned long long>(clock64() - t1));     // boxes, conversion, tensor-memory stores
+          atomicAdd(prof_p + 3, 1ull);
         }
       }
       // hand the group's remaining boxes back so the producer can go on with the next group
@@ -410,19 +448,22 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
     }
   } else {
     // ---------------- epilogue warps 0-3: thread = TMEM lane = channel ----------------
+    // Each warp stages and stores its own 32 channels (TMA boxes of [32 channels x 32 samples] out of its quarter of the
+    // staging tiles): no barrier between the four warps, only the mbarriers towards the MMA warp.
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const int r = warp * 32 + lane;
     const uint32_t row_addr0 = smem_u32(stage) + static_cast<uint32_t>(r) * 128u;
     const uint32_t rx = static_cast<uint32_t>(r & 7);
+    unsigned char* const warp_stage = stage + warp * (32 * 128);
     uint32_t kk = 0, n_box = 0;      // boxes stored so far: box n goes through staging tile n mod kStages
     // the start state of the coming chunk, x 2^6 and split in three fp16 pieces, to tensor memory
+    constexpr bool kStateMma = kUseStateMma && 5 * kS <= 64;
     auto hand_over = [&](const float (&s)[kS]) {
-      uint32_t w[3][8];
+      uint32_t w[3][kS / 2];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float v0 = 0.f, v1 = 0.f;
-        if (2 * c < kS) { v0 = s[2 * c] * a.s_scale; v1 = s[2 * c + 1] * a.s_scale; }
+      for (int c = 0; c < kS / 2; ++c) {
+        const float v0 = s[2 * c] * a.s_scale, v1 = s[2 * c + 1] * a.s_scale;
         w[0][c] = pack_h2(v0, v1);
         const float2 f1 = unpack_h2(w[0][c]);
         const float r0 = v0 - f1.x, r1 = v1 - f1.y;
@@ -430,22 +471,31 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
         const float2 f2 = unpack_h2(w[1][c]);
         w[2][c] = pack_h2(r0 - f2.x, r1 - f2.y);
       }
+      uint32_t cols[32];
 #pragma unroll
-      for (int p = 0; p < 3; ++p) tmem_st8(lane_base + kColS + 8 * p, w[p]);
+      for (int c = 0; c < 32; ++c) {
+        if constexpr (kStateMma) {       // [s1 | s2 | s3 | s1 | s2 | 0], kS fp16 each
+          const int q = c / (kS / 2);
+          cols[c] = q < 5 ? w[q % 3][c % (kS / 2)] : 0u;
+        } else {                         // [s1 | s2 | s3 | unused], 16 fp16 each
+          cols[c] = (c < 24 && (c % 8) < kS / 2) ? w[c / 8][c % 8] : 0u;
+        }
+      }
+      tmem_st16(lane_base + kColS, cols);
+      tmem_st16(lane_base + kColS + 16, cols + 16);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_ready);
     };
-    // pieces [p0, p1) of the chunk (16 bytes each) into the staging tile at piece position pp0..; the tile must be free
+    // the warp's store that last used the coming staging tile has read it
     auto wait_stage = [&]() {
       long long tw = 0;
-      const bool pw = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+      const bool pw = prof_p != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
       if (pw) tw = clock64();
-      if (threadIdx.x == 0)      // the store that last used the coming tile has read it
-        asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStages - 1) : "memory");
-      epi_bar();
-      if (pw) atomicAdd(a.prof + 16, static_cast<unsigned long long>(clock64() - tw));
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStages - 1) : "memory");
+      __syncwarp();
+      if (pw) atomicAdd(prof_p + 16, static_cast<unsigned long long>(clock64() - tw));
     };
     for (int gi = 0; gi < n_local; ++gi) {
       const int g = static_cast<int>(blockIdx.x) + gi * static_cast<int>(gridDim.x);
@@ -454,7 +504,7 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
       for (int i = 0; i < kS; ++i) s[i] = 0.f;
       for (int k = 0; k < a.n_chunks; ++k, ++kk) {
         const uint32_t buf = kk & 1;
-        const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+        const bool prof = prof_p != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         if (prof) t0 = clock64();
         mbar_wait(&acc_full[buf], (kk >> 1) & 1);
@@ -471,7 +521,10 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         if (prof) t2 = clock64();
         // the next chunk's start state first: the MMA warp is waiting for it
-        {
+        if constexpr (kStateMma) {      // the accumulator's state columns already hold Phi s + K x
+#pragma unroll
+          for (int i = 0; i < kS; ++i) s[i] = __uint_as_float(v[5][i]) * a.unscale;
+        } else {
           float u[kS];
 #pragma unroll
           for (int i = 0; i < kS; ++i) u[i] = __uint_as_float(v[5][i]) * a.unscale;
@@ -481,31 +534,32 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
         if (prof) t2b = clock64();
         if (k + 1 < a.n_chunks) hand_over(s);
         if (prof) t3 = clock64();
-        if (prof) atomicAdd(a.prof + 15, static_cast<unsigned long long>(t3 - t2b));   // of "state": the hand-over
+        if (prof) atomicAdd(prof_p + 15, static_cast<unsigned long long>(t3 - t2b));   // of "state": the hand-over
         // unscale, clip, stage, store.  Two chunks = 160 outputs = five boxes of 32: an even chunk fills boxes 0, 1 and the
         // first half of box 2 of its pair, the odd chunk the rest.
-        auto put = [&](int p, uint32_t pp) {   // piece p of the chunk (outputs 4p .. 4p+3) to piece position pp of the staging row
-          float o[4];
+        auto put4 = [&](int q, uint32_t pp0) {   // pieces 4q .. 4q+3 (outputs 16q .. 16q+15) to piece positions pp0 .. pp0+3 of the staging row
+          float o[16];
 #pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const float2 m = fmul2s(make_float2(__uint_as_float(v[p >> 2][(p & 3) * 4 + e]), __uint_as_float(v[p >> 2][(p & 3) * 4 + e + 1])),
-                                    a.unscale);
+          for (int e = 0; e < 16; e += 2) {
+            const float2 m = fmul2s(make_float2(__uint_as_float(v[q][e]), __uint_as_float(v[q][e + 1])), a.unscale);
             o[e] = m.x;
             o[e + 1] = m.y;
           }
           if (a.clip) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = clip_unit(o[e]);
+            for (int e = 0; e < 16; ++e) o[e] = clip_unit(o[e]);
           }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                       ::"r"(row_addr0 + (n_box % kStages) * kBoxBytes + ((pp ^ rx) << 4)), "f"(o[0]), "f"(o[1]),
-                         "f"(o[2]), "f"(o[3]) : "memory");
+          const uint32_t base = row_addr0 + (n_box % kStages) * kBoxBytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(base + (((pp0 + j) ^ rx) << 4)), "f"(o[4 * j]), "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3]) : "memory");
         };
         auto send = [&](int box) {
           fence_proxy_async();
-          epi_bar();
-          if (threadIdx.x == 0) {
-            tma_store_2d(&tm_z, stage + (n_box % kStages) * kBoxBytes, box * 32, g * kTM);
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_z, warp_stage + (n_box % kStages) * kBoxBytes, box * 32, g * kTM + warp * 32);
             tma_store_commit();
           }
           ++n_box;
@@ -516,34 +570,34 @@ xz_mma_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ 
         const uint32_t end_mask = (k & 1) ? 0x80808u : (k + 1 == a.n_chunks ? 0x88080u : 0x08080u);   // even: 7, 15 (+ 19 when the signal ends here: the hardware clips the rest)
         int box = 5 * (k >> 1) + ((k & 1) ? 2 : 0);
 #pragma unroll
-        for (int p = 0; p < 20; ++p) {
-          if ((p & 3) == 0 && ((start_mask >> p) & 1u)) wait_stage();
-          put(p, (static_cast<uint32_t>(p) + off) & 7u);
-          if ((p & 3) == 3 && ((end_mask >> p) & 1u)) send(box++);
+        for (int q = 0; q < 5; ++q) {
+          if ((start_mask >> (4 * q)) & 1u) wait_stage();
+          put4(q, (static_cast<uint32_t>(4 * q) + off) & 7u);
+          if ((end_mask >> (4 * q + 3)) & 1u) send(box++);
         }
         if (prof) {
-          atomicAdd(a.prof + 4, static_cast<unsigned long long>(t1 - t0));           // waiting for the accumulator
-          atomicAdd(a.prof + 5, static_cast<unsigned long long>(t2 - t1));           // tensor memory -> registers
-          atomicAdd(a.prof + 6, static_cast<unsigned long long>(t3 - t2));           // state update + hand-over
-          atomicAdd(a.prof + 7, static_cast<unsigned long long>(clock64() - t3));    // clip + staging + stores
-          atomicAdd(a.prof + 8, 1ull);
+          atomicAdd(prof_p + 4, static_cast<unsigned long long>(t1 - t0));           // waiting for the accumulator
+          atomicAdd(prof_p + 5, static_cast<unsigned long long>(t2 - t1));           // tensor memory -> registers
+          atomicAdd(prof_p + 6, static_cast<unsigned long long>(t3 - t2));           // state update + hand-over
+          atomicAdd(prof_p + 7, static_cast<unsigned long long>(clock64() - t3));    // clip + staging + stores
+          atomicAdd(prof_p + 8, 1ull);
         }
       }
     }
-    if (threadIdx.x == 0) tma_store_wait_all0();
-    if (a.prof != nullptr && threadIdx.x == 0) {
+    if (lane == 0) tma_store_wait_all0();
+    if (prof_p != nullptr && threadIdx.x == 0) {
       unsigned long long g1;
       unsigned smid;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
       asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
       if (blockIdx.x == 0) {
-        a.prof[20] = static_cast<unsigned long long>(clock64() - prof_c0);
-        a.prof[21] = g1 - prof_g0;
+        prof_p[20] = static_cast<unsigned long long>(clock64() - prof_c0);
+        prof_p[21] = g1 - prof_g0;
       }
       if (blockIdx.x < 160) {      // per CTA: start and end time (ns), SM
-        a.prof[32 + 3 * blockIdx.x] = prof_g0;
-        a.prof[33 + 3 * blockIdx.x] = g1;
-        a.prof[34 + 3 * blockIdx.x] = smid;
+        prof_p[32 + 3 * blockIdx.x] = prof_g0;
+        prof_p[33 + 3 * blockIdx.x] = g1;
+        prof_p[34 + 3 * blockIdx.x] = smid;
       }
     }
   }
@@ -561,8 +615,13 @@ size_t xz_smem_bytes(const XzPlan& xp) {
 template <int kS>
 int launch(const CUtensorMap& tm_g, const CUtensorMap& tm_x, const CUtensorMap& tm_z, const XzArgs& a, size_t smem, int grid,
            cudaStream_t stream) {
-  DSP_CUDA(cudaFuncSetAttribute(xz_mma_kernel<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  xz_mma_kernel<kS><<<grid, kThreads, smem, stream>>>(tm_g, tm_x, tm_z, a);
+  if (a.prof != nullptr) {
+    DSP_CUDA(cudaFuncSetAttribute(xz_mma_kernel<kS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    xz_mma_kernel<kS, true><<<grid, kThreads, smem, stream>>>(tm_g, tm_x, tm_z, a);
+  } else {
+    DSP_CUDA(cudaFuncSetAttribute(xz_mma_kernel<kS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    xz_mma_kernel<kS, false><<<grid, kThreads, smem, stream>>>(tm_g, tm_x, tm_z, a);
+  }
   return after_launch("xz_mma_kernel");
 }
 
@@ -610,8 +669,12 @@ int xz_build(const std::vector<double>& taps, int L, int M, const Section* sec, 
         gmax = std::fmax(gmax, std::fabs(v));
       }
   }
+  const int ks = (n + 3) / 4 * 4;                       // states padded to a multiple of 4
+  const bool state_mma = kUseStateMma && 5 * ks <= 64;  // see the kernel: the state advances inside the free-response MMAs
   double omax = 0.0;
   for (double v : cs.o) omax = std::fmax(omax, std::fabs(v));
+  if (state_mma)
+    for (double v : cs.phi) omax = std::fmax(omax, std::fabs(v));
   if (!(gmax > 0.0) || !std::isfinite(gmax) || !std::isfinite(omax)) return DSPB200_OK;
   const int ge = static_cast<int>(std::floor(std::log2(8192.0 / gmax)));       // |G 2^ge| in [4096, 8192)
   const int oe = kXScaleExp + ge - kSScaleExp;                                  // O' = O 2^oe, state pieces x 2^6
@@ -644,7 +707,7 @@ int xz_build(const std::vector<double>& taps, int L, int M, const Section* sec, 
         rows_total += static_cast<uint32_t>(kND - xp.blk_row0[ph][b]);
       }
   xp.o_off = rows_total * 128u;
-  rows_total += kC;
+  rows_total += state_mma ? kND : kC;
   xp.tab_rows = static_cast<int>(rows_total);
   xp.tab_bytes = rows_total * 128u;
   std::vector<__half> tab(static_cast<size_t>(rows_total) * 64, __float2half_rn(0.f));
@@ -667,13 +730,18 @@ int xz_build(const std::vector<double>& taps, int L, int M, const Section* sec, 
           tab[(xp.blk_off[ph][0][b] / 128 + rr) * 64 + static_cast<size_t>(c)] = hi;
           tab[(xp.blk_off[ph][1][b] / 128 + rr) * 64 + static_cast<size_t>(c)] = lo;
         }
-  // [s1 | s2 | s3 | s1] . [O_hi | O_hi | O_hi | O_lo]^T, 16 state slots per piece
-  for (int r = 0; r < kC; ++r)
+  // free-response operand, 96 rows: outputs 0..79 take O, and (state_mma) rows 80.. take Phi, so that the same MMAs advance the
+  // state.  K layout: [s1 | s2 | s3 | s1 | s2] . [hi | hi | hi | lo | lo] with ks fp16 per piece, or, for more than 12
+  // states, [s1 | s2 | s3 | s1] . [hi | hi | hi | lo] with 16 per piece (the s2 . lo term, 2^-22 relative, is dropped there)
+  for (int r = 0; r < (state_mma ? kC + n : kC); ++r)
     for (int i = 0; i < n; ++i) {
+      const double v = r < kC ? cs.o[static_cast<size_t>(r) * kLtiMaxStates + i]
+                              : cs.phi[static_cast<size_t>(r - kC) * kLtiMaxStates + i];
       __half hi, lo;
-      split(cs.o[static_cast<size_t>(r) * kLtiMaxStates + i] * os, hi, lo);
+      split(v * os, hi, lo);
       __half* row = &tab[(xp.o_off / 128 + static_cast<size_t>(r)) * 64];
-      row[i] = hi; row[16 + i] = hi; row[32 + i] = hi; row[48 + i] = lo;
+      if (state_mma) { row[i] = hi; row[ks + i] = hi; row[2 * ks + i] = hi; row[3 * ks + i] = lo; row[4 * ks + i] = lo; }
+      else { row[i] = hi; row[16 + i] = hi; row[32 + i] = hi; row[48 + i] = lo; }
     }
   for (int i = 0; i < kLtiMaxStates * kLtiMaxStates; ++i) {
     xp.phi[i] = static_cast<float>(cs.phi[static_cast<size_t>(i)]);
@@ -682,7 +750,7 @@ int xz_build(const std::vector<double>& taps, int L, int M, const Section* sec, 
   if (!finite) return DSPB200_OK;
   DSP_CUDA(cudaMalloc(reinterpret_cast<void**>(&xp.d_table), tab.size() * sizeof(__half)));
   DSP_CUDA(cudaMemcpy(xp.d_table, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  xp.states = (n + 3) / 4 * 4;
+  xp.states = ks;
   xp.unscale = static_cast<float>(std::ldexp(1.0, -(kXScaleExp + ge)));
   xp.first_new = static_cast<int>(start[0]) + kHalo;
   xp.start0 = static_cast<int>(start[0]);
@@ -725,7 +793,7 @@ int xz_run(const XzPlan& xp, const float* x, int64_t xs, float* z, int64_t zs, i
   DSP_TRY(encode_tmap_2d(&tm_x, DSPB200_F32, x, static_cast<uint64_t>(n_in), static_cast<uint64_t>(channels),
                          static_cast<uint64_t>(xs) * sizeof(float), 32, kTM, true));
   DSP_TRY(encode_tmap_2d(&tm_z, DSPB200_F32, z, static_cast<uint64_t>(n_out), static_cast<uint64_t>(channels),
-                         static_cast<uint64_t>(zs) * sizeof(float), 32, kTM, true));
+                         static_cast<uint64_t>(zs) * sizeof(float), 32, 32, true));     // one store per epilogue warp
   XzArgs a{};
   a.channels = channels; a.n_in = n_in; a.n_out = n_out;
   a.n_chunks = static_cast<int>(ceil_div(n_out, kC));

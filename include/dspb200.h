@@ -227,7 +227,9 @@ int dspb200_fft_c2c_host_f64(const dspb200_fft_plan* plan, const double* in, dou
  * reads x once and writes z once (xz_mma.cu; DSPB200_CHAIN_NO_FUSED=1 in the
  * environment disables it, DSPB200_CHAIN_FORCE_FUSED=1 uses it at any batch
  * width); otherwise the resampler writes into z and the equaliser runs in
- * place.  The fused form needs |x| < 1023 (fp16 operand pieces).
+ * place.  The fused form needs |x| < 1023 (fp16 operand pieces); its stores
+ * are clipped at 16-byte granularity, which never leaves a row of the dense
+ * z (n_out % 4 == 0 is a condition of the form).
  * `workspace` only serves long FFTs (dspb200_fft_workspace_bytes). */
 int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_fft_plan* fft,
                                   int64_t channels, int64_t n_in, int keep_y, size_t* bytes);

@@ -692,6 +692,193 @@ def test_chain_c5_shape_slice(pk, torch_cuda):
     assert float(((ef - et).abs() / et).max()) <= 1e-4
 
 
+# ------------------------------------------------- fused SRC->EQ (xz_mma) ----
+def _chain_ref(x_row, gains_or_sections, L=160, M=147, fs=44100):
+    """float64 oracle of SRC -> EQ for one channel; gains dict or [(fc, gain_db)] list"""
+    y, fs2 = o.resample_closed_form(x_row.astype(np.float64), fs, M, L)
+    if isinstance(gains_or_sections, dict):
+        return o.equalizer(y, fs2, gains_or_sections)
+    for fc, g in gains_or_sections:
+        y = o.difference_equation(y, *o.peaking_biquad(fc, fs2, g))
+    return np.clip(y, -1, 1)
+
+
+@pytest.mark.parametrize("gains", [C1_GAINS, (15,) * 6, (-15,) * 6, (0, 0, 0, 0, 0, 12), (3, 0, -2, 0, 0, 5),
+                                   (-12.0412, 15, -12.5, 6, 0, -3)])
+def test_chain_fused_matches_oracle(pk, torch_cuda, gains):
+    """The one-kernel SRC->EQ form (fp16 three-product split on tcgen05, y never written) against the float64 oracle
+    and against the three-kernel cascade: 1..6 sections (4, 8 and 12 padded states), real and complex poles, a batch
+    that ends inside a channel group, an output length that ends inside a chunk and inside a 32-sample store box."""
+    torch = torch_cuda
+    gd = gains_dict(gains)
+    ch = pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float32)
+    rng = np.random.default_rng(7)
+    channels, n_in = 130, 22052
+    x = rng.uniform(-0.5, 0.5, (channels, n_in)).astype(np.float32)
+    xt = torch.as_tensor(x, device="cuda")
+    z = ch.run_fused(xt)
+    assert z.shape == (channels, ch.out_len(n_in)) and not bool(torch.isnan(z).any())
+    y = ch.src.run(xt)
+    z3 = ch.eq.run(y)
+    assert float((z - z3).abs().max()) <= TOL_F32_EQ
+    zc = z.cpu().numpy()
+    for c in (0, 31, 32, 127, 128, 129):
+        assert o.full_scale_err(zc[c], _chain_ref(x[c], gd)) <= TOL_F32_EQ, (gains, c)
+
+
+@pytest.mark.parametrize("n_sections", [7, 8])
+def test_chain_fused_sixteen_states(pk, torch_cuda, n_sections):
+    """Cascades of 7 and 8 sections (16 padded states: the widest variant of the fused kernel)."""
+    torch = torch_cuda
+    centres = [60.0, 250.0, 700.0, 1500.0, 3200.0, 6000.0, 9000.0, 14000.0][:n_sections]
+    gains = [5.0, -4.0, 7.5, -6.0, 3.0, -9.0, 12.0, -2.5][:n_sections]
+    ch = pk.Chain(160, 147, 44100, gains_dict(C1_GAINS), n_fft=4096, dtype=np.float32)
+    ch.eq = pk.EqPlan(ch.fs_out, list(zip(centres, gains)), np.float32)
+    rng = np.random.default_rng(n_sections)
+    x = rng.uniform(-0.4, 0.4, (64, 9000)).astype(np.float32)
+    z = ch.run_fused(torch.as_tensor(x, device="cuda")).cpu().numpy()
+    for c in (0, 63):
+        assert o.full_scale_err(z[c], _chain_ref(x[c], list(zip(centres, gains)))) <= TOL_F32_EQ, (n_sections, c)
+
+
+@pytest.mark.parametrize("n_in", [41, 147, 300, 4412, 22049])
+def test_chain_fused_lengths(pk, torch_cuda, n_in):
+    """Short and ragged lengths: from the shortest long-signal input (41 samples: 41 * 160 >= 6401 taps) up; one chunk,
+    an odd number of chunks, outputs that are not a multiple of 4 (rows padded by the caller)."""
+    torch = torch_cuda
+    gd = gains_dict(C1_GAINS)
+    ch = pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float32)
+    rng = np.random.default_rng(n_in)
+    x = rng.uniform(-1.0, 1.0, (3, n_in)).astype(np.float32)
+    pitch = -(-n_in // 4) * 4
+    xt = torch.zeros((3, pitch), device="cuda")[:, :n_in]
+    xt.copy_(torch.as_tensor(x))
+    n_out = ch.out_len(n_in)
+    guard = torch.full((3, -(-n_out // 4) * 4 + 8), 7.0, device="cuda")
+    z = ch.run_fused(xt, out=guard[:, :n_out])
+    # TMA stores clip at 16-byte granularity: the row's own padding up to a multiple of 4 samples may be written,
+    # nothing beyond it
+    assert bool((guard[:, -(-n_out // 4) * 4:] == 7.0).all())
+    for c in range(3):
+        assert o.full_scale_err(z[c].cpu().numpy(), _chain_ref(x[c], gd)) <= TOL_F32_EQ, (n_in, c)
+
+
+def test_chain_fused_more_groups_than_sms_and_dispatch(pk, torch_cuda, monkeypatch):
+    """19000 channels = 149 groups of 128 on 148 SMs (one CTA walks two groups: ring, window and staging state carry
+    over), picked by Chain.run on its own; narrow batches and float64 stay on the three-kernel cascade; the
+    environment switches; identical results through run() and run_fused()."""
+    torch = torch_cuda
+    gd = gains_dict(C1_GAINS)
+    ch = pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float32)
+    assert ch.kernel_kind(19000, 7644) == "fused" and ch.kernel_kind(1024, 441000) == "cascade"
+    assert ch.kernel_kind(19000, 2000) == "cascade"          # 2177 outputs: the dense z rows would not be 16-byte aligned
+    assert pk.Chain(3, 2, 44100, gd, n_fft=4096, dtype=np.float32).kernel_kind(19000, 7644) == "cascade"
+    assert pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float64).kernel_kind(19000, 7644) == "cascade"
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((19000, 7644), generator=gen, device="cuda") - 0.5
+    _, z, mag = ch.run(x)
+    assert torch.equal(z, ch.run_fused(x))
+    monkeypatch.setenv("DSPB200_CHAIN_NO_FUSED", "1")
+    assert ch.kernel_kind(19000, 7644) == "cascade"
+    _, z3, mag3 = ch.run(x)
+    monkeypatch.delenv("DSPB200_CHAIN_NO_FUSED")
+    assert float((z - z3).abs().max()) <= TOL_F32_EQ
+    m_ref = float(mag3.abs().max())
+    assert float((mag - mag3).abs().max()) <= 1e-4 * m_ref
+    for c in (0, 127, 128, 18943, 18944, 18999):
+        assert o.full_scale_err(z[c].cpu().numpy(), _chain_ref(x[c].cpu().numpy(), gd)) <= TOL_F32_EQ, c
+    monkeypatch.setenv("DSPB200_CHAIN_FORCE_FUSED", "1")
+    assert ch.kernel_kind(8, 7644) == "fused"
+    monkeypatch.delenv("DSPB200_CHAIN_FORCE_FUSED")
+    # keep_y needs y: always the cascade, and its z agrees with the fused one
+    y, zk, _ = ch.run(x[:300], keep_y=True)
+    assert y is not None and float((zk - z[:300]).abs().max()) <= TOL_F32_EQ
+
+
+def test_chain_fused_linearity_and_full_clip_length(pk, torch_cuda):
+    """C5's clip length on 256 clips through the fused kernel: oracle on two clips; linearity of the unclipped cascade
+    (all gains negative keeps |z| < 1): z(a x1 + b x2) = a z(x1) + b z(x2)."""
+    torch = torch_cuda
+    gd = gains_dict((-3, -4, -2, -6, -3, -9))
+    ch = pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float32)
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    x1 = 0.4 * (torch.rand((256, 441000), generator=gen, device="cuda") - 0.5)
+    x2 = 0.4 * (torch.rand((256, 441000), generator=gen, device="cuda") - 0.5)
+    z1, z2 = ch.run_fused(x1), ch.run_fused(x2)
+    z12 = ch.run_fused(0.75 * x1 - 1.25 * x2)
+    assert float(z12.abs().max()) < 1.0
+    assert float((z12 - (0.75 * z1 - 1.25 * z2)).abs().max()) <= 1e-5
+    for c in (0, 255):
+        assert o.full_scale_err(z1[c].cpu().numpy(), _chain_ref(x1[c].cpu().numpy(), gd)) <= TOL_F32_EQ
+
+
+def test_tensor_forms_nonfinite_inputs_stay_local_in_time(pk, torch_cuda, monkeypatch):
+    """Documented deviation of the tensor-core forms: a non-finite input sample poisons the whole chunk it falls in
+    (96 samples in the EQ kernel, 80 outputs in the fused chain kernel) and, through the recurrence, everything after
+    it -- the reference (lfilter) only the samples from it on.  Samples before the chunk are untouched in both."""
+    torch = torch_cuda
+    gd = gains_dict(C1_GAINS)
+    plan = pk.EqPlan.from_gains(48000, gd, np.float32)
+    x = torch.rand((4, 960), device="cuda") - 0.5
+    x[2, 500] = float("nan")
+    monkeypatch.setenv("DSPB200_EQ_FORCE_MMA", "1")
+    z = plan.run(x)
+    monkeypatch.delenv("DSPB200_EQ_FORCE_MMA")
+    monkeypatch.setenv("DSPB200_EQ_NO_MMA", "1")
+    z_scan = plan.run(x)
+    monkeypatch.delenv("DSPB200_EQ_NO_MMA")
+    bad = torch.isnan(z[2]).nonzero().flatten()
+    bad_scan = torch.isnan(z_scan[2]).nonzero().flatten()
+    assert int(bad_scan.min()) == 500                                   # sequential form: from the sample on, like lfilter
+    assert int(bad.min()) == 480 and int(bad.max()) == 959              # tensor form: from the start of its 96-sample chunk
+    assert not bool(torch.isnan(z[[0, 1, 3]]).any())
+    assert float((z[2, :480] - z_scan[2, :480]).abs().max()) <= TOL_F32_EQ
+    ch = pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float32)
+    xc = torch.rand((4, 4412), device="cuda") - 0.5
+    xc[1, 2000] = float("inf")
+    zf = ch.run_fused(xc)
+    first = int((~torch.isfinite(zf[1])).nonzero().flatten().min())
+    # input 2000 first reaches output ceil((2000 * 160 - 3200) / 147) = 2156; its chunk starts at 2080 (the k-step that holds
+    # the sample skips the chunk's first coefficient rows, so the poison starts somewhere inside the chunk)
+    assert 2080 <= first <= 2156
+    assert bool(torch.isfinite(zf[[0, 2, 3]]).all())
+
+
+def test_wrong_plan_handles_are_rejected(pk, torch_cuda):
+    """Plans carry a type tag: an entry point handed another plan type (or a destroyed plan) answers an error code
+    (ValueError through the shim) instead of reading the wrong layout."""
+    import ctypes as C
+    from dsp_audio_project_b200 import _lib
+    torch = torch_cuda
+    lib = _lib.load()
+    src = pk.SrcPlan(3, 2, np.float32)
+    eq = pk.EqPlan.from_gains(48000, gains_dict(C1_GAINS), np.float32)
+    fft = pk.FftPlan(256, np.float32)
+    x = torch.rand((2, 512), device="cuda")
+    out = torch.empty((2, 1024), device="cuda")
+    state = torch.zeros((2, 16), device="cuda")
+    args = (x.data_ptr(), 512, out.data_ptr(), 1024, 2, 512)
+    assert lib.dspb200_eq_run_f32(src._h, *args, None) == _lib.ERR_INVALID
+    assert "not a live eq plan" in _lib.last_error()
+    assert lib.dspb200_eq_run_stream_f32(src._h, *args, state.data_ptr(), 1, None) == _lib.ERR_INVALID
+    assert lib.dspb200_src_run_f32(eq._h, *args, None) == _lib.ERR_INVALID
+    assert lib.dspb200_src_run_f32(fft._h, *args, None) == _lib.ERR_INVALID
+    ws = C.c_size_t()
+    assert lib.dspb200_fft_workspace_bytes(eq._h, 4, C.byref(ws)) == _lib.ERR_INVALID
+    k = C.c_int()
+    assert lib.dspb200_chain_kernel_kind(eq._h, src._h, 4, 512, 512, C.byref(k)) == _lib.ERR_INVALID
+    assert lib.dspb200_eq_plan_destroy(fft._h) == _lib.ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(lib.dspb200_fftmag_run_f32(src._h, x.data_ptr(), 512, 512, 0, 256, 2, out.data_ptr(), 129, 258, 2, None, 0, None))
+    assert not hasattr(pk.SrcPlan, "run_stream")           # the resampler has no streaming form
+    # plans that own device tables refuse to run with another device current
+    if torch.cuda.device_count() > 1:
+        x1 = torch.rand((2, 512), device="cuda:1")
+        with torch.cuda.device(1):
+            rc = lib.dspb200_src_run_f32(src._h, x1.data_ptr(), 512, x1.data_ptr(), 512, 2, 300, None)
+        assert rc == _lib.ERR_INVALID and "built on device 0" in _lib.last_error()
+
+
 def test_library_reports_launches(pk):
     from dsp_audio_project_b200 import _lib
     assert _lib.launch_count() > 0
