@@ -46,12 +46,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="chain", choices=["chain", "src", "eq", "fft"])
-    ap.add_argument("--clips", type=int, default=18944, help="clips (channels) per GPU per step")
+    ap.add_argument("--workload", default="chain", choices=["chain", "c5job", "src", "eq", "fft"])
+    ap.add_argument("--clips", type=int, default=18944, help="clips (channels) per GPU per step / per wave")
+    ap.add_argument("--job-clips", type=int, default=262144, help="c5job: clips of the whole job (all GPUs)")
     ap.add_argument("--e2e-clips", type=int, default=1024, help="clips per host-buffer call of the e2e leg")
+    ap.add_argument("--f64-clips", type=int, default=4736, help="clips of the float64 sub-line (N=1 only)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-f64", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -147,7 +151,7 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------
 def workload_config(args):
-    return {
+    cfg = {
         "workload": "C5 chain, one wave shaped as C2: clips x 10 s @44.1 kHz -> SRC 160/147 -> 6-band EQ "
                     "(gains 6,-3,4,-6,3,-9 dB) -> 4096-pt Hann |FFT| frames",
         "selected": args.workload, "clips_per_gpu": args.clips, "clip_samples": CLIP_SAMPLES,
@@ -156,6 +160,12 @@ def workload_config(args):
         "l2": "inputs per step exceed the 126 MB L2 (no flush needed)",
         "parallelism": f"channel-sharded x{args.gpus}, no collective",
     }
+    if args.workload == "c5job":
+        cfg["workload"] = ("C5 job: %d clips x 10 s @44.1 kHz in all, sharded by clip over the GPUs, processed in waves of "
+                           "<= %d clips generated on the device by dspb200_generate_uniform_f32 inside the timed region "
+                           "-> SRC 160/147 -> 6-band EQ -> 4096-pt Hann |FFT| frames" % (args.job_clips, args.clips))
+        cfg["job_clips"] = args.job_clips
+    return cfg
 
 
 class ClockSampler:
@@ -238,13 +248,34 @@ def traffic_from_profiles(kernel, clips):
         return None
 
 
+FP64_TFMA_PEAK = 17.9      # measured on B200 with tools/microbench.cu (DFMA issue rate, round 1): 35.8 TFLOP/s
+
+
+def oracle_spot_check(x_rows, z_rows, mag_rows):
+    """float64 oracle (closed-form polyphase SRC, lfilter cascade, recursive FFT frames) of whole clips of the timed
+    wave, compared with what the timed kernels left in z / mag.  Returns the worst errors in the tests' measures."""
+    import numpy as np
+    from oracle import dsp_oracle as o
+
+    ez, em = 0.0, 0.0
+    for x, z, m in zip(x_rows, z_rows, mag_rows):
+        yo, fs2 = o.resample_closed_form(np.asarray(x, dtype=np.float64), FS_IN, M_DOWN, L_UP)
+        zo = o.equalizer(yo, fs2, GAINS)
+        ez = max(ez, o.full_scale_err(z, zo))
+        frames = [0, 58, 116]
+        for f in frames:
+            mo = o.frame_magnitudes(zo[f * N_FFT:(f + 1) * N_FFT], N_FFT)[0]
+            em = max(em, o.rel_err(m[f], mo))
+    return ez, em
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import dsp_audio_project_b200 as pkg
-    from dsp_audio_project_b200 import _lib
+    from dsp_audio_project_b200 import _lib, shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
@@ -273,39 +304,72 @@ def run_b200(args):
     np_dt = np.float32 if args.dtype == "f32" else np.float64
     t_dt = torch.float32 if args.dtype == "f32" else torch.float64
     esize = 4 if args.dtype == "f32" else 8
-    clips = args.clips
     chain = pkg.Chain(L_UP, M_DOWN, FS_IN, GAINS, n_fft=N_FFT, dtype=np_dt)
     n_out = chain.out_len(CLIP_SAMPLES)
     n_frames = n_out // N_FFT
     bins = N_FFT // 2 + 1
 
-    gen = torch.Generator(device=dev).manual_seed(4 + rank)
-    x = (torch.rand((clips, CLIP_SAMPLES), generator=gen, device=dev, dtype=t_dt) - 0.5)
+    # ---- this rank's share of the work and its waves --------------------------------------------------------------
+    if args.workload == "c5job":
+        c0, c1 = shard.channel_block(args.job_clips, world, rank)
+        my_clips = c1 - c0
+        n_waves = max(1, -(-my_clips // args.clips))
+        per = -(-my_clips // n_waves)
+        per = -(-per // 128) * 128                       # whole groups of 128 channels: what the tensor-core kernels walk
+        waves = []
+        at = c0
+        while at < c1:
+            waves.append((at, min(per, c1 - at)))
+            at += per
+        clips = max(w[1] for w in waves) if waves else 0
+        scaling = "strong"
+    else:
+        clips = args.clips
+        waves = [(rank * clips, clips)]
+        scaling = "weak"
 
-    # persistent device buffers so every step reuses the same memory; as in dspb200_chain_run the EQ runs in place
-    # on the SRC output (config C5 keeps z and the spectra, y is never materialised on its own)
-    y = torch.empty((clips, n_out), dtype=t_dt, device=dev)
-    z = y
+    # persistent device buffers so every step reuses the same memory.  Config C5 keeps z and the spectra; y is never
+    # materialised: the fused kernel goes from x to z, the cascade writes y into z and equalises in place
+    x = torch.empty((clips, CLIP_SAMPLES), dtype=t_dt, device=dev)
+    z = torch.empty((clips, n_out), dtype=t_dt, device=dev)
     mag = torch.empty((clips, n_frames, bins), dtype=t_dt, device=dev)
+    seed = 4 + rank                                      # seed 4 + rank
+
+    def generate(first, count):
+        pkg.generate_uniform(x[:count], seed, -0.5, 0.5, first_channel=first)
+
+    generate(*waves[0])
+    kind = chain.kernel_kind(clips, CLIP_SAMPLES)
 
     def step_chain():
-        chain.src.run(x, out=y)
-        chain.eq.run(y, out=z)
-        chain.fft.magnitudes(z, out=mag)
+        chain.run(x, z=z, mag=mag)
+
+    def step_job():
+        for first, count in waves:
+            generate(first, count)
+            chain.run(x[:count], z=z[:count], mag=mag[:count])
+
+    def step_srceq():
+        if kind == "fused":
+            chain.run_fused(x, out=z)
+        else:
+            chain.src.run(x, out=z)
+            chain.eq.run(z, out=z)
 
     def step_src():
-        chain.src.run(x, out=y)
+        chain.src.run(x, out=z)
 
     def step_eq():
-        chain.eq.run(y, out=z)
+        chain.eq.run(z, out=z)
 
     def step_fft():
         chain.fft.magnitudes(z, out=mag)
 
-    step = {"chain": step_chain, "src": step_src, "eq": step_eq, "fft": step_fft}[args.workload]
-    step_chain()                      # populate y, z for the single-kernel workloads
+    step = {"chain": step_chain, "c5job": step_job, "src": step_src, "eq": step_eq, "fft": step_fft}[args.workload]
+    step_chain()                      # populate z for the single-kernel workloads
     torch.cuda.synchronize()
-    samples_per_step = {"chain": clips * CLIP_SAMPLES, "src": clips * CLIP_SAMPLES,
+    my_total = sum(w[1] for w in waves)
+    samples_per_step = {"chain": clips * CLIP_SAMPLES, "c5job": my_total * CLIP_SAMPLES, "src": clips * CLIP_SAMPLES,
                         "eq": clips * n_out, "fft": clips * n_frames * N_FFT}[args.workload]
 
     def barrier():
@@ -328,11 +392,15 @@ def run_b200(args):
     barrier()
     launches = _lib.launch_count() - launches0
     ms = e0.elapsed_time(e1)
-    # per-kernel timing (same stream, events between the launches)
-    names = ["src", "eq", "fft"]
-    fns = [step_src, step_eq, step_fft]
+    # per-kernel timing (same stream, events between the launches), on the wave the buffers hold
+    if args.workload == "c5job":
+        generate(*waves[0])
+    if kind == "fused" and args.workload in ("chain", "c5job"):
+        names, fns = ["src_eq", "fft"], [step_srceq, step_fft]
+    else:
+        names, fns = ["src", "eq", "fft"], [step_src, step_eq, step_fft]
     per_kernel = {k: 0.0 for k in names}
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)] for _ in range(args.steps)]
     for it in range(args.steps):
         evs[it][0].record()
         for j, fn in enumerate(fns):
@@ -344,15 +412,80 @@ def run_b200(args):
         for j, k in enumerate(names):
             per_kernel[k] += evs[it][j].elapsed_time(evs[it][j + 1]) / args.steps
 
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(samples_per_step)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * samples_per_step * args.steps / (ms_max * 1e-3) / 1e6
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_samples = float(t[1].item())
+    else:
+        total_samples = float(samples_per_step)
+    ms_max = float(tmax[0].item())
+    value = total_samples * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- parity of the timed wave itself: two whole clips against the float64 oracle (outside the timed region) -----
+    parity = None
+    if rank == 0 and not args.no_parity and args.workload in ("chain", "c5job") and args.dtype == "f32":
+        step_chain()
+        torch.cuda.synchronize()
+        rows = [0, clips - 1]
+        ez, em = oracle_spot_check([x[r].cpu().numpy() for r in rows], [z[r].cpu().numpy() for r in rows],
+                                   [mag[r].cpu().numpy() for r in rows])
+        parity = {"z_full_scale": ez, "mag_rel": em, "clips": rows, "frames_checked": [0, 58, 116],
+                  "tolerance": {"z_full_scale": 1e-4, "mag_rel": 1e-4},
+                  "against": "oracle/dsp_oracle.py (float64: closed-form polyphase SRC, lfilter cascade, recursive FFT)"}
+
+    # ---- float64 sub-line: the reference's own arithmetic type, parity kernels, N = 1 only ---------------------------
+    f64_line = None
+    if (rank == 0 and world == 1 and not args.no_f64 and args.workload == "chain" and args.dtype == "f32"
+            and args.f64_clips > 0):
+        c64 = min(args.f64_clips, clips)
+        ch64 = pkg.Chain(L_UP, M_DOWN, FS_IN, GAINS, n_fft=N_FFT, dtype=np.float64)
+        x64 = torch.empty((c64, CLIP_SAMPLES), dtype=torch.float64, device=dev)
+        pkg.generate_uniform(x64, seed, -0.5, 0.5)
+        z64 = torch.empty((c64, n_out), dtype=torch.float64, device=dev)
+        m64 = torch.empty((c64, n_frames, bins), dtype=torch.float64, device=dev)
+        f_names = ["src", "eq", "fft"]
+        f_fns = [lambda: ch64.src.run(x64, out=z64), lambda: ch64.eq.run(z64, out=z64),
+                 lambda: ch64.fft.magnitudes(z64, out=m64)]
+        for _ in range(2):
+            for fn in f_fns:
+                fn()
+        f_steps = 3
+        fe = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(f_steps)]
+        for it in range(f_steps):
+            fe[it][0].record()
+            for j, fn in enumerate(f_fns):
+                fn()
+                fe[it][j + 1].record()
+        torch.cuda.synchronize()
+        peak, _ = measured_hbm_peak()
+        f_bytes = {"src": 8 * c64 * (CLIP_SAMPLES + n_out), "eq": 8 * c64 * 2 * n_out,
+                   "fft": 8 * c64 * n_frames * (N_FFT + bins)}
+        # float64 FMAs the reference's arithmetic needs: 40.006 per resampler output, 9 flop per
+        # sample and section of the cascade (5 mul + 4 add: 5 FMA-pipe instructions), 2.5 N log2 N flop per frame
+        f_fma = {"src": 40.006 * c64 * n_out, "eq": 6 * 5.0 * c64 * n_out,
+                 "fft": 1.25 * N_FFT * 12 * c64 * n_frames}
+        f_k = {}
+        tot = 0.0
+        for j, k in enumerate(f_names):
+            msk = sum(fe[it][j].elapsed_time(fe[it][j + 1]) for it in range(f_steps)) / f_steps
+            tot += msk
+            hbm_ms = f_bytes[k] / (peak * 1e9) * 1e3
+            pipe_ms = f_fma[k] / (FP64_TFMA_PEAK * 1e12) * 1e3
+            f_k[k] = {"ms": msk, "hbm_floor_ms": hbm_ms, "fp64_pipe_floor_ms": pipe_ms,
+                      "bound": "hbm" if hbm_ms >= pipe_ms else "fp64_pipe", "frac_of_bound": max(hbm_ms, pipe_ms) / msk,
+                      "frac_of_hbm": hbm_ms / msk}
+        f64_line = {"dtype": "f64", "clips": c64, "ms_per_step": tot,
+                    "value": c64 * CLIP_SAMPLES / (tot * 1e-3) / 1e6, "unit": "Msamples/s", "kernels": f_k,
+                    "fp64_pipe_peak_tfma": FP64_TFMA_PEAK,
+                    "note": "three float64 kernels (tiled SRC, scan EQ, FFT); floors: algorithmic bytes / measured HBM peak "
+                            "and reference FMAs / measured DFMA rate; parity <= 1e-10 relative (tests)"}
+        del x64, z64, m64
 
     # ---- e2e: host-buffer C-ABI call, copies inside the timed region -------
     e2e = None
-    if not args.no_e2e and args.workload == "chain":
+    if not args.no_e2e and args.workload in ("chain", "c5job"):
         ec = max(1, min(args.e2e_clips, clips))
         xh = torch.empty((ec, CLIP_SAMPLES), dtype=t_dt, pin_memory=True)
         xh.copy_(x[:ec])
@@ -366,52 +499,83 @@ def run_b200(args):
         for _ in range(e2e_steps):
             chain.run_host(xa, za, ma)
         dt_host = time.perf_counter() - t0
-        th = torch.tensor([dt_host], dtype=torch.float64, device=dev)
+        # the same bytes with no kernels at all: what the host<->device fabric alone allows (both directions at once)
+        dxc, dzc, dmc = x[:ec], z[:ec], mag[:ec]
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            with torch.cuda.stream(s_in):
+                dxc.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                zh.copy_(dzc, non_blocking=True)
+                mh.copy_(dmc, non_blocking=True)
+            torch.cuda.synchronize()
+        dt_copy = time.perf_counter() - t0
+        th = torch.tensor([dt_host, dt_copy], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(th, op=dist.ReduceOp.MAX)
-        dt_host = float(th.item())
+        dt_host, dt_copy = float(th[0].item()), float(th[1].item())
         e2e = {"value": world * ec * CLIP_SAMPLES * e2e_steps / dt_host / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": ec * CLIP_SAMPLES * esize,
                "d2h_bytes_per_step": (ec * n_out + ec * n_frames * bins) * esize,
                "steps": e2e_steps, "ms_per_step": dt_host / e2e_steps * 1e3, "clips_per_step": ec,
-               "api": "dspb200_chain_host_f32 (pinned host buffers, 3-stream slab pipeline)"}
-        # the host path must reproduce the device path bit for bit
-        if rank == 0:
-            # (narrow host slabs run the FFMA forms of SRC/EQ, the wide device wave the tensor-core forms:
-            # the two agree to the fp32 parity bound, not bit for bit)
-            e2e["max_abs_diff_vs_device_path"] = float((zh[:4].to(dev) - z[:4]).abs().max())
+               "api": "dspb200_chain_host_f32 (pinned host buffers, 3-stream slab pipeline)",
+               "copy_only_ms_per_step": dt_copy / e2e_steps * 1e3, "frac_of_copy_ceiling": dt_copy / dt_host}
+        if rank == 0 and not args.no_parity and args.dtype == "f32":
+            # the host form's own output against the oracle (narrow slabs run the FFMA kernels, not the tensor-core ones)
+            ez, em = oracle_spot_check([xa[0]], [za[0]], [ma[0]])
+            e2e["parity_err"] = {"z_full_scale": ez, "mag_rel": em, "clips": [0]}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         alg_bytes = {
             "src": esize * clips * (CLIP_SAMPLES + n_out),
             "eq": esize * clips * 2 * n_out,
+            "src_eq": esize * clips * (CLIP_SAMPLES + n_out),
             "fft": esize * clips * n_frames * (N_FFT + bins),
         }
-        src_kind = chain.src.kernel_kind(clips, CLIP_SAMPLES) if getattr(chain, "src", None) is not None else "tiled"
-        eq_kind = chain.eq.kernel_kind(clips, n_out) if getattr(chain, "eq", None) is not None else "scan"
+        src_kind = chain.src.kernel_kind(clips, CLIP_SAMPLES)
+        eq_kind = chain.eq.kernel_kind(clips, n_out)
         kernel_names = {"src": "src_mma_kernel" if src_kind == "tensor" else "src_tiled_kernel",
-                        "eq": "lti_mma_kernel" if eq_kind == "tensor" else "eq_packed_kernel", "fft": "fft_fixed_kernel"}
+                        "eq": "lti_mma_kernel" if eq_kind == "tensor" else "eq_packed_kernel",
+                        "src_eq": "xz_mma_kernel", "fft": "fft_fixed_kernel"}
         kernels = {}
         for k in names:
             gbs = alg_bytes[k] / (per_kernel[k] * 1e-3) / 1e9
             kernels[k] = {"kernel": kernel_names[k], "ms": per_kernel[k], "algorithmic_bytes": alg_bytes[k],
                           "achieved_gbs": gbs, "frac": gbs / peak, "traffic": traffic_from_profiles(kernel_names[k], clips)}
-        dom = max(names, key=lambda k: per_kernel[k]) if args.workload == "chain" else args.workload
+        dom = max(names, key=lambda k: per_kernel[k]) if args.workload in ("chain", "c5job") else args.workload
         line = {
-            "metric": "Msamples/s SRC->EQ->FFT chain" if args.workload == "chain" else f"Msamples/s {args.workload}",
+            "metric": "Msamples/s SRC->EQ->FFT chain" if args.workload in ("chain", "c5job") else f"Msamples/s {args.workload}",
             "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
             "roofline": {"bound": "hbm", "kernel": kernels[dom]["kernel"], "achieved": kernels[dom]["achieved_gbs"],
                          "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
                          "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
                          "ms_per_launch": kernels[dom]["ms"]},
-            "kernels": kernels,
+            "kernels": kernels, "chain_kind": kind,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": e2e,
         }
+        if args.workload in ("chain", "c5job"):
+            # the whole chain against SURVEY.md 8d's C5 bytes: x read once, z and the spectra written once
+            chain_bytes = esize * (CLIP_SAMPLES + n_out + n_frames * bins)          # 4.643 MB per clip in float32
+            step_clips = clips if args.workload == "chain" else my_total
+            ms_chain = sum(per_kernel.values()) if args.workload == "chain" else ms_max / args.steps
+            gbs = chain_bytes * step_clips / (ms_chain * 1e-3) / 1e9
+            line["roofline"]["chain"] = {"algorithmic_bytes_per_clip": chain_bytes, "clips": step_clips, "ms": ms_chain,
+                                         "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                         "note": "z is written by the SRC->EQ kernel and read back by the FFT kernel: "
+                                                 "1.41x the algorithmic bytes move; with the generator's writes in c5job"}
+        if args.workload == "c5job":
+            line["waves"] = [{"first_clip": w[0], "clips": w[1]} for w in waves]
+        if parity is not None:
+            line["parity_err"] = parity
+        if f64_line is not None:
+            line["f64"] = f64_line
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
         emit(line)

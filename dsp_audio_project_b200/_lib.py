@@ -76,6 +76,8 @@ SIGNATURES = {
     "dspb200_pcm16_run_f64": (C.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_mono_normalize_run_f64": (C.c_int, [c_p, c_i64, c_i64, C.c_int, c_p, c_i64, c_p, c_p]),
     "dspb200_mono_normalize_run_f32": (C.c_int, [c_p, c_i64, c_i64, C.c_int, c_p, c_i64, c_p, c_p]),
+    "dspb200_generate_uniform_f32": (C.c_int, [c_p, c_i64, c_i64, c_i64, c_i64, C.c_uint64, C.c_double, C.c_double, c_p]),
+    "dspb200_generate_uniform_f64": (C.c_int, [c_p, c_i64, c_i64, c_i64, c_i64, C.c_uint64, C.c_double, C.c_double, c_p]),
     "dspb200_launch_count": (C.c_int64, []),
 }
 # test hooks exported by the library but not part of the public header

@@ -259,8 +259,75 @@ static int mono_run(const TI* in, int64_t clips, int64_t frames, int cin, float*
 
 using namespace dspb200;
 
+// ---- synthetic clips for the throughput configurations ("generated on device per wave") -------------
+// x[c, i] = lo + (hi - lo) * u,  u = top 24 bits of splitmix64(seed + golden * (c * n + i + 1)) / 2^24: counter based, so a
+// wave is reproducible on the host (tests) whatever the launch shape.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// lo + span * u with two roundings (no contraction into an FMA), so that the numpy twin reproduces it bit for bit
+__device__ __forceinline__ float affine_rn(float lo, float span, float u) { return __fadd_rn(lo, __fmul_rn(span, u)); }
+__device__ __forceinline__ double affine_rn(double lo, double span, double u) { return __dadd_rn(lo, __dmul_rn(span, u)); }
+template <typename T>
+__global__ void __launch_bounds__(256)
+generate_uniform_kernel(T* __restrict__ x, long long stride, long long channels, long long n, long long first_channel,
+                        unsigned long long seed, T lo, T span) {
+  const long long quads = (n + 3) / 4;
+  for (long long c = blockIdx.y; c < channels; c += gridDim.y) {
+    T* row = x + c * stride;
+    const unsigned long long base = static_cast<unsigned long long>(first_channel + c) * static_cast<unsigned long long>(n);
+    for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < quads; q += static_cast<long long>(gridDim.x) * blockDim.x) {
+      T v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned long long h = splitmix64(seed + 0x9E3779B97F4A7C15ull * (base + static_cast<unsigned long long>(4 * q + e) + 1ull));
+        v[e] = affine_rn(lo, span, static_cast<T>(static_cast<unsigned>(h >> 40)) * static_cast<T>(1.0 / 16777216.0));
+      }
+      if (4 * q + 3 < n && (reinterpret_cast<uintptr_t>(row + 4 * q) % (4 * sizeof(T))) == 0) {
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(row + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          *reinterpret_cast<double2*>(row + 4 * q) = make_double2(v[0], v[1]);
+          *reinterpret_cast<double2*>(row + 4 * q + 2) = make_double2(v[2], v[3]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e < n) row[4 * q + e] = v[e];
+      }
+    }
+  }
+}
+
+template <typename T>
+static int generate_run(T* x, int64_t stride, int64_t channels, int64_t n, int64_t first_channel, uint64_t seed, double lo,
+                        double hi, cudaStream_t stream) {
+  DSP_CHECK(channels >= 0 && n >= 0 && first_channel >= 0, "negative shape");
+  if (channels == 0 || n == 0) return DSPB200_OK;
+  DSP_CHECK(x != nullptr, "NULL buffer");
+  DSP_CHECK(stride >= n, "channel stride smaller than n");
+  DSP_TRY(ensure_device());
+  const long long quads = (n + 3) / 4;
+  const long long per_row = ceil_div(quads, 256);
+  const long long want_x = per_row < 64 ? per_row : 64;
+  dim3 grid(static_cast<unsigned>(want_x > 0 ? want_x : 1), static_cast<unsigned>(channels < 16384 ? channels : 16384));
+  generate_uniform_kernel<T><<<grid, 256, 0, stream>>>(x, stride, channels, n, first_channel, seed, static_cast<T>(lo),
+                                                        static_cast<T>(hi - lo));
+  return after_launch("generate_uniform_kernel");
+}
+
 extern "C" {
 
+int dspb200_generate_uniform_f32(float* x, int64_t stride, int64_t channels, int64_t n, int64_t first_channel, uint64_t seed,
+                                 double lo, double hi, void* stream) {
+  return generate_run<float>(x, stride, channels, n, first_channel, seed, lo, hi, static_cast<cudaStream_t>(stream));
+}
+int dspb200_generate_uniform_f64(double* x, int64_t stride, int64_t channels, int64_t n, int64_t first_channel, uint64_t seed,
+                                 double lo, double hi, void* stream) {
+  return generate_run<double>(x, stride, channels, n, first_channel, seed, lo, hi, static_cast<cudaStream_t>(stream));
+}
 int dspb200_pcm16_run_f32(const float* x, int64_t stride, float* peaks, int16_t* out, int64_t out_stride,
                           int64_t rows, int64_t n, void* stream) {
   return pcm16_run<float>(x, stride, peaks, out, out_stride, rows, n, static_cast<cudaStream_t>(stream));

@@ -512,6 +512,21 @@ def mono_normalize(frames):
     return mono, peaks
 
 
+def generate_uniform(out, seed: int, lo: float = -0.5, hi: float = 0.5, first_channel: int = 0):
+    """Fill a [channels, n] CUDA tensor with the library's counter-based synthetic clips (the throughput configurations
+    generate their inputs on the device wave by wave); oracle.dsp_oracle.synthetic_clips is the numpy twin
+    the tests check it against."""
+    torch = _torch()
+    dtype_id = _dtype_id(out.dtype)
+    _check_tensor(out, dtype_id, "out")
+    ch, n = out.shape
+    fn = _lib.load().dspb200_generate_uniform_f32 if dtype_id == F32 else _lib.load().dspb200_generate_uniform_f64
+    with torch.cuda.device(out.device):
+        check(fn(out.data_ptr(), _row_stride(out), ch, n, int(first_channel), int(seed) & (2 ** 64 - 1), float(lo), float(hi),
+                 _stream_ptr(out)))
+    return out
+
+
 @functools.lru_cache(maxsize=32)
 def cached_src_plan(L: int, M: int, dtype_id: int) -> SrcPlan:
     return SrcPlan(L, M, _np_dtype(dtype_id))

@@ -274,6 +274,15 @@ int dspb200_mono_normalize_run_f64(const double* in, int64_t clips, int64_t fram
 int dspb200_mono_normalize_run_f32(const float* in, int64_t clips, int64_t frames, int channels_in, float* mono,
                                    int64_t mono_stride, float* peaks, void* stream);
 
+/* Synthetic clips for the throughput configurations (inputs are
+ * generated on the device wave by wave).  x[c, i] = lo + (hi - lo) * u with
+ * u = (splitmix64(seed + 0x9E3779B97F4A7C15 * ((first_channel + c) * n + i + 1)) >> 40) / 2^24:
+ * counter based, reproducible on the host. */
+int dspb200_generate_uniform_f32(float* x, int64_t stride, int64_t channels, int64_t n, int64_t first_channel,
+                                 uint64_t seed, double lo, double hi, void* stream);
+int dspb200_generate_uniform_f64(double* x, int64_t stride, int64_t channels, int64_t n, int64_t first_channel,
+                                 uint64_t seed, double lo, double hi, void* stream);
+
 /* Number of kernels this library has launched on the calling process since
  * load (bench.py's gpu_launches). */
 int64_t dspb200_launch_count(void);

@@ -351,6 +351,23 @@ def pcm16_export(z):
     return (y * 32767).astype(np.int16)
 
 
+def synthetic_clips(channels: int, n: int, seed: int, lo: float = -0.5, hi: float = 0.5, first_channel: int = 0,
+                          dtype=np.float32):
+    """numpy restatement of the library's on-device clip generator (dspb200_generate_uniform_*, csrc/post.cu: splitmix64
+    of a per-sample counter, top 24 bits): not reference behaviour, only how the throughput configurations of
+    SURVEY.md 8d make their inputs, so that the tests can reproduce a device-generated wave on the host."""
+    idx = (np.arange(first_channel, first_channel + channels, dtype=np.uint64)[:, None] * np.uint64(n)
+           + np.arange(1, n + 1, dtype=np.uint64)[None, :])
+    with np.errstate(over="ignore"):
+        z = np.uint64(int(seed) & (2 ** 64 - 1)) + np.uint64(0x9E3779B97F4A7C15) * idx
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    dt = np.dtype(dtype)
+    u = (z >> np.uint64(40)).astype(dt) * dt.type(1.0 / 16777216.0)
+    return (dt.type(lo) + dt.type(hi - lo) * u).astype(dt)
+
+
 def rel_err(a, ref) -> float:
     """max|a-ref| / max|ref| (the north star's relative error)."""
     a = np.asarray(a)
