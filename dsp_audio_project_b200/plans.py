@@ -514,8 +514,8 @@ def mono_normalize(frames):
 
 def generate_uniform(out, seed: int, lo: float = -0.5, hi: float = 0.5, first_channel: int = 0):
     """Fill a [channels, n] CUDA tensor with the library's counter-based synthetic clips (the throughput configurations
-    generate their inputs on the device wave by wave); oracle.dsp_oracle.synthetic_clips is the numpy twin
-    the tests check it against."""
+    generate their inputs on the device wave by wave); the tests hold a numpy twin of the generator
+    (synthetic_clips) and check this kernel against it."""
     torch = _torch()
     dtype_id = _dtype_id(out.dtype)
     _check_tensor(out, dtype_id, "out")
