@@ -526,6 +526,45 @@ def run_b200(args):
             # the host form's own output against the oracle (narrow slabs run the FFMA kernels, not the tensor-core ones)
             ez, em = oracle_spot_check([xa[0]], [za[0]], [ma[0]])
             e2e["parity_err"] = {"z_full_scale": ez, "mag_rel": em, "clips": [0]}
+        # the export form of the same call: z leaves as the int16 signal app.py:349-354 writes to the WAV and the
+        # spectra as the dB values app.py:207-210 plots -> 2/3 of the device-to-host bytes
+        chain_db = pkg.Chain(L_UP, M_DOWN, FS_IN, GAINS, n_fft=N_FFT, dtype=np_dt, db=True)
+        qh = torch.empty((ec, n_out), dtype=torch.int16, pin_memory=True)
+        ph = torch.empty((ec,), dtype=t_dt, pin_memory=True)
+        qa, pa = qh.numpy(), ph.numpy()
+        chain_db.run_host_pcm16(xa, qa, ma, pa)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            chain_db.run_host_pcm16(xa, qa, ma, pa)
+        dt_exp = time.perf_counter() - t0
+        dq = torch.empty((ec, n_out), dtype=torch.int16, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            with torch.cuda.stream(s_in):
+                dxc.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                qh.copy_(dq, non_blocking=True)
+                mh.copy_(dmc, non_blocking=True)
+            torch.cuda.synchronize()
+        dt_copy2 = time.perf_counter() - t0
+        th = torch.tensor([dt_exp, dt_copy2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        dt_exp, dt_copy2 = float(th[0].item()), float(th[1].item())
+        e2e["export"] = {"value": world * ec * CLIP_SAMPLES * e2e_steps / dt_exp / 1e6, "unit": "Msamples/s",
+                         "h2d_bytes_per_step": ec * CLIP_SAMPLES * esize,
+                         "d2h_bytes_per_step": ec * n_out * 2 + ec * esize + ec * n_frames * bins * esize,
+                         "ms_per_step": dt_exp / e2e_steps * 1e3,
+                         "api": "dspb200_chain_host_pcm16_f32 (z as int16 per app.py:349-354, dB spectra per app.py:207-210)",
+                         "copy_only_ms_per_step": dt_copy2 / e2e_steps * 1e3, "frac_of_copy_ceiling": dt_copy2 / dt_exp}
+        if rank == 0 and not args.no_parity and args.dtype == "f32":
+            from oracle import dsp_oracle as o
+            ref_q = o.pcm16_export(za[0].astype(np.float64)).astype(np.int32)
+            e2e["export"]["parity_err"] = {"pcm16_lsb": int(np.max(np.abs(qa[0].astype(np.int32) - ref_q))), "clips": [0],
+                                           "against": "oracle pcm16_export of the float32 z the plain call returned"}
+        del dq
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()

@@ -71,6 +71,8 @@ SIGNATURES = {
     "dspb200_chain_kernel_kind": (C.c_int, [c_p, c_p, c_i64, c_i64, c_i64, _pi]),
     "dspb200_chain_host_f32": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dspb200_chain_host_f64": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "dspb200_chain_host_pcm16_f32": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p]),
+    "dspb200_chain_host_pcm16_f64": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "dspb200_host_release": (C.c_int, []),
     "dspb200_pcm16_run_f32": (C.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
     "dspb200_pcm16_run_f64": (C.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_i64, c_i64, c_p]),

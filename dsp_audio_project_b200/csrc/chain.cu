@@ -118,11 +118,12 @@ struct HostPipe {
   static constexpr int kStreams = 3;
   int device = -1;
   cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
-  void* buf[kStreams][4] = {};          // x, z, mag, workspace
-  size_t cap[kStreams][4] = {};
+  static constexpr int kBufs = 6;
+  void* buf[kStreams][kBufs] = {};      // x, z, mag, workspace, int16 z, row peaks
+  size_t cap[kStreams][kBufs] = {};
   void release() {
     for (int i = 0; i < kStreams; ++i) {
-      for (int j = 0; j < 4; ++j) { if (buf[i][j]) cudaFree(buf[i][j]); buf[i][j] = nullptr; cap[i][j] = 0; }
+      for (int j = 0; j < kBufs; ++j) { if (buf[i][j]) cudaFree(buf[i][j]); buf[i][j] = nullptr; cap[i][j] = 0; }
       if (st[i]) cudaStreamDestroy(st[i]);
       st[i] = nullptr;
     }
@@ -142,10 +143,13 @@ static thread_local HostPipe g_pipe;
 
 template <typename T>
 static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
-                      const T* x, int64_t channels, int64_t n_in, T* z, T* mag) {
+                      const T* x, int64_t channels, int64_t n_in, T* z, T* mag, int16_t* z_pcm = nullptr,
+                      T* peaks = nullptr) {
+  // z_pcm != NULL: the export form.  z stays on the device; what crosses PCIe is the int16 signal app.py:349-354
+  // writes to the WAV (half the bytes of float32 z) and, optionally, the per-clip peaks it was divided by.
   DSP_CHECK(channels >= 0 && n_in >= 1, "bad shape");
   if (channels == 0) return DSPB200_OK;
-  DSP_CHECK(x != nullptr && z != nullptr, "NULL buffer");
+  DSP_CHECK(x != nullptr && (z != nullptr || z_pcm != nullptr), "NULL buffer");
   DSP_TRY(ensure_device());
   int64_t slab = 32;   // measured: 32-channel slabs pipeline best against PCIe (63 ms vs 65 ms at 64, 68 ms at 128 per 1024-clip wave)
   if (const char* e = getenv("DSPB200_CHAIN_SLAB")) {
@@ -171,6 +175,8 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
   T* dz[kStreams] = {nullptr, nullptr, nullptr};
   T* dm[kStreams] = {nullptr, nullptr, nullptr};
   void* dw[kStreams] = {nullptr, nullptr, nullptr};
+  int16_t* dq[kStreams] = {nullptr, nullptr, nullptr};
+  T* dp[kStreams] = {nullptr, nullptr, nullptr};
   const size_t ws_bytes = s.fft_ws;
   const size_t mag_elems = static_cast<size_t>(slab) * s.n_frames * s.bins;
   cudaError_t e = cudaSuccess;
@@ -181,6 +187,10 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
     if (e == cudaSuccess) e = hp.ensure(i, 1, static_cast<size_t>(slab) * s.n_out * sizeof(T));
     if (e == cudaSuccess && mag_elems && mag) e = hp.ensure(i, 2, mag_elems * sizeof(T));
     if (e == cudaSuccess && ws_bytes) e = hp.ensure(i, 3, ws_bytes);
+    if (e == cudaSuccess && z_pcm) e = hp.ensure(i, 4, static_cast<size_t>(slab) * round_up(s.n_out, 8) * sizeof(int16_t));
+    if (e == cudaSuccess && z_pcm) e = hp.ensure(i, 5, static_cast<size_t>(slab) * sizeof(T));
+    dq[i] = z_pcm ? static_cast<int16_t*>(hp.buf[i][4]) : nullptr;
+    dp[i] = z_pcm ? static_cast<T*>(hp.buf[i][5]) : nullptr;
     dx[i] = static_cast<T*>(hp.buf[i][0]);
     dz[i] = static_cast<T*>(hp.buf[i][1]);
     dm[i] = (mag_elems && mag) ? static_cast<T*>(hp.buf[i][2]) : nullptr;
@@ -195,8 +205,22 @@ static int chain_host(const dspb200_src_plan* src, const dspb200_eq_plan* eq, co
     if (e != cudaSuccess) break;
     rc = chain_run<T>(src, eq, fft, dx[i], xp, nc, n_in, nullptr, dz[i], dm[i], dw[i], ws_bytes, st[i]);
     if (rc != DSPB200_OK) break;
-    e = cudaMemcpyAsync(z + c0 * s.n_out, dz[i], static_cast<size_t>(nc) * s.n_out * sizeof(T),
-                        cudaMemcpyDeviceToHost, st[i]);
+    if (z_pcm) {
+      const int64_t qp = round_up(s.n_out, 8);     // 16-byte aligned int16 rows on the device
+      rc = pcm16_run<T>(dz[i], s.n_out, dp[i], dq[i], qp, nc, s.n_out, st[i]);
+      if (rc != DSPB200_OK) break;
+      if (qp == s.n_out)
+        e = cudaMemcpyAsync(z_pcm + c0 * s.n_out, dq[i], static_cast<size_t>(nc) * s.n_out * sizeof(int16_t),
+                            cudaMemcpyDeviceToHost, st[i]);
+      else
+        e = cudaMemcpy2DAsync(z_pcm + c0 * s.n_out, s.n_out * sizeof(int16_t), dq[i], qp * sizeof(int16_t),
+                              s.n_out * sizeof(int16_t), nc, cudaMemcpyDeviceToHost, st[i]);
+      if (e == cudaSuccess && peaks)
+        e = cudaMemcpyAsync(peaks + c0, dp[i], static_cast<size_t>(nc) * sizeof(T), cudaMemcpyDeviceToHost, st[i]);
+    }
+    if (e == cudaSuccess && z)
+      e = cudaMemcpyAsync(z + c0 * s.n_out, dz[i], static_cast<size_t>(nc) * s.n_out * sizeof(T),
+                          cudaMemcpyDeviceToHost, st[i]);
     if (e == cudaSuccess && dm[i])
       e = cudaMemcpyAsync(mag + c0 * s.n_frames * s.bins, dm[i],
                           static_cast<size_t>(nc) * s.n_frames * s.bins * sizeof(T), cudaMemcpyDeviceToHost, st[i]);
@@ -277,6 +301,18 @@ int dspb200_chain_fused_f32(const dspb200_src_plan* src, const dspb200_eq_plan* 
 int dspb200_chain_host_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
                            const float* x, int64_t channels, int64_t n_in, float* z, float* mag) {
   return chain_host<float>(src, eq, fft, x, channels, n_in, z, mag);
+}
+int dspb200_chain_host_pcm16_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                                 const float* x, int64_t channels, int64_t n_in, int16_t* z_pcm, float* peaks,
+                                 float* mag) {
+  DSP_CHECK(z_pcm != nullptr, "z_pcm is NULL");
+  return chain_host<float>(src, eq, fft, x, channels, n_in, nullptr, mag, z_pcm, peaks);
+}
+int dspb200_chain_host_pcm16_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                                 const double* x, int64_t channels, int64_t n_in, int16_t* z_pcm, double* peaks,
+                                 double* mag) {
+  DSP_CHECK(z_pcm != nullptr, "z_pcm is NULL");
+  return chain_host<double>(src, eq, fft, x, channels, n_in, nullptr, mag, z_pcm, peaks);
 }
 int dspb200_host_release(void) {
   g_pipe.release();

@@ -20,6 +20,10 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
                int64_t hop, int64_t n_frames, T* mag, int64_t mfs, int64_t mcs, int64_t channels,
                void* ws, size_t ws_bytes, cudaStream_t stream);
 int src_plan_ratio(const dspb200_src_plan* plan, int* L, int* M, int* dtype);
+// playback export (post.cu; app.py:349-354): row peaks, then int16(trunc(nan_to_num(x) / peak * 32767))
+template <typename T>
+int pcm16_run(const T* x, int64_t stride, T* peaks, short* out, int64_t out_stride, int64_t rows, int64_t n,
+              cudaStream_t stream);
 
 // K1 on tcgen05 (src_mma.cu): per-plan tap matrices and the launch.  fp32 only.
 struct SrcMmaPlan {

@@ -210,8 +210,8 @@ static void tile_rows(long long rows, long long n, long long& chunk, dim3& grid)
 }
 
 template <typename T>
-static int pcm16_run(const T* x, int64_t stride, T* peaks, short* out, int64_t out_stride, int64_t rows, int64_t n,
-                     cudaStream_t stream) {
+int pcm16_run(const T* x, int64_t stride, T* peaks, short* out, int64_t out_stride, int64_t rows, int64_t n,
+              cudaStream_t stream) {
   DSP_CHECK(rows >= 0 && n >= 0, "negative shape");
   if (rows == 0 || n == 0) return DSPB200_OK;
   DSP_CHECK(x && peaks && out, "NULL buffer");
@@ -231,6 +231,9 @@ static int pcm16_run(const T* x, int64_t stride, T* peaks, short* out, int64_t o
   else pcm16_kernel<T, false><<<grid, 256, 0, stream>>>(x, stride, peaks, out, out_stride, rows, n, chunk);
   return after_launch("pcm16_kernel");
 }
+template int pcm16_run<float>(const float*, int64_t, float*, short*, int64_t, int64_t, int64_t, cudaStream_t);
+template int pcm16_run<double>(const double*, int64_t, double*, short*, int64_t, int64_t, int64_t, cudaStream_t);
+
 
 template <typename TI>
 static int mono_run(const TI* in, int64_t clips, int64_t frames, int cin, float* mono, int64_t mono_stride,

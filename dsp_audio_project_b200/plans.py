@@ -10,6 +10,7 @@ twiddles/window) and is immutable after creation.  Two call styles:
 from __future__ import annotations
 
 import ctypes as C
+import math
 import functools
 
 import numpy as np
@@ -317,6 +318,17 @@ class FftPlan:
         hop = self.n_fft if hop is None else int(hop)
         return 0 if n - offset < self.n_fft else (n - offset - self.n_fft) // hop + 1
 
+    def first_bin_above(self, fs: float, f_min: float = 0.5) -> int:
+        """app.py:207 keeps the bins with rfftfreq(n_fft, 1/fs) > 0.5 before the dB conversion.  The bin frequencies
+        k*fs/n_fft rise with k, so that mask is the suffix starting at the bin returned here (1 for any practical
+        fs/n_fft: only DC goes): ``spectra[..., plan.first_bin_above(fs):]`` is the masked spectrum as a view."""
+        k = int(math.floor(f_min * self.n_fft / float(fs))) + 1 if f_min >= 0 else 0
+        while k > 0 and (k - 1) * float(fs) / self.n_fft > f_min:
+            k -= 1
+        while k < self.bins and k * float(fs) / self.n_fft <= f_min:
+            k += 1
+        return min(k, self.bins)
+
     def magnitudes(self, x, *, hop=None, offset: int = 0, n_frames=None, n_valid=None, out=None):
         """|FFT(hann * frame)|[:n_fft/2+1] for frames of x [channels, time] ->
         [channels, n_frames, bins].  Samples at or beyond n_valid read as zero."""
@@ -380,13 +392,14 @@ class FftPlan:
 class Chain:
     """SRC -> EQ -> framed magnitude spectra (app.py:161-167, :202-205)."""
 
-    def __init__(self, L: int, M: int, fs_in: float, gains: dict, n_fft: int = 4096, dtype=np.float32):
+    def __init__(self, L: int, M: int, fs_in: float, gains: dict, n_fft: int = 4096, dtype=np.float32,
+                 db: bool = False):
         self.dtype_id = _dtype_id(dtype)
         self.L, self.M = int(L), int(M)
         self.src = None if (self.L == 1 and self.M == 1) else SrcPlan(L, M, dtype)
         self.fs_out = int(fs_in * self.L / self.M)  # dsp_core.py:172
         self.eq = EqPlan.from_gains(self.fs_out, gains, dtype)
-        self.fft = FftPlan(n_fft, dtype, hann=True)
+        self.fft = FftPlan(n_fft, dtype, hann=True, db=db)   # db: spectra leave as 20 log10(|X| + 1e-12), app.py:207-210
         self._ws = None
 
     def out_len(self, n_in):
@@ -464,6 +477,29 @@ class Chain:
         check(fn(self.src._h if self.src else None, self.eq._h if self.eq else None, self.fft._h,
                  a.ctypes.data, ch, n_in, z.ctypes.data, mag.ctypes.data))
         return z, mag
+
+    def run_host_pcm16(self, x, z_pcm=None, mag=None, peaks=None):
+        """Export form of run_host: z comes back as the int16 signal app.py:349-354 hands to the WAV writer (peak
+        normalised per clip, truncated), half the PCIe bytes of float32 z; returns (z_pcm, peaks, mag).  Build the
+        chain with db=True for the dB spectra of app.py:207-210."""
+        a = x if (isinstance(x, np.ndarray) and x.flags.c_contiguous and x.dtype == _np_dtype(self.dtype_id)
+                  and x.ndim == 2) else _as_host(x, self.dtype_id)
+        ch, n_in = a.shape
+        n_out = self.out_len(n_in)
+        n_frames = n_out // self.fft.n_fft
+        if z_pcm is None:
+            z_pcm = np.empty((ch, n_out), dtype=np.int16)
+        if peaks is None:
+            peaks = np.empty((ch,), dtype=a.dtype)
+        if mag is None:
+            mag = np.empty((ch, n_frames, self.fft.bins), dtype=a.dtype)
+        if z_pcm.dtype != np.int16 or z_pcm.shape != (ch, n_out) or not z_pcm.flags.c_contiguous:
+            raise ValueError(f"z_pcm must be a contiguous int16 [{ch}, {n_out}] array")
+        lib = _lib.load()
+        fn = lib.dspb200_chain_host_pcm16_f32 if self.dtype_id == F32 else lib.dspb200_chain_host_pcm16_f64
+        check(fn(self.src._h if self.src else None, self.eq._h if self.eq else None, self.fft._h,
+                 a.ctypes.data, ch, n_in, z_pcm.ctypes.data, peaks.ctypes.data, mag.ctypes.data))
+        return z_pcm, peaks, mag
 
 
 def to_pcm16(z, out=None):

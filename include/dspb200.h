@@ -254,6 +254,20 @@ int dspb200_chain_host_f64(const dspb200_src_plan* src, const dspb200_eq_plan* e
                            const dspb200_fft_plan* fft, const double* x, int64_t channels,
                            int64_t n_in, double* z, double* mag);
 
+/* Export form of the host cascade: what app.py does with z after the chain
+ * (app.py:349-354: nan_to_num, divide by the clip's peak when it is > 0, times
+ * 32767, truncate to int16) runs on the device, so the signal crosses PCIe as
+ * int16 (half the bytes of float32 z).  z_pcm: dense [channels, n_out] int16;
+ * peaks: [channels] values of the working type (the divisors; may be NULL);
+ * mag as above -- build the FFT plan with DSPB200_FFT_DB for the dB spectra of
+ * app.py:207-210 -- and may be NULL. */
+int dspb200_chain_host_pcm16_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq,
+                                 const dspb200_fft_plan* fft, const float* x, int64_t channels,
+                                 int64_t n_in, int16_t* z_pcm, float* peaks, float* mag);
+int dspb200_chain_host_pcm16_f64(const dspb200_src_plan* src, const dspb200_eq_plan* eq,
+                                 const dspb200_fft_plan* fft, const double* x, int64_t channels,
+                                 int64_t n_in, int16_t* z_pcm, double* peaks, double* mag);
+
 /* The host form keeps its streams and device slabs per calling thread between
  * calls; this frees the calling thread's. */
 int dspb200_host_release(void);

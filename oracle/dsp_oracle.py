@@ -288,7 +288,7 @@ def magnitude_spectrum(x, fs):
     return freqs[:keep], mag[:keep]
 
 
-def frame_magnitudes(x, n_fft: int, hop: int | None = None, offset: int = 0):
+def frame_magnitudes(x, n_fft: int, hop: int | None = None, offset: int = 0, n_frames: int | None = None):
     """Framing rule fixed in SURVEY.md 8d for the throughput configs: frames of
     n_fft samples every ``hop`` (default n_fft) starting at ``offset``, tail
     dropped; each frame is |FFT(frame*hann)|[:n_fft/2+1] with the reference's
@@ -298,7 +298,8 @@ def frame_magnitudes(x, n_fft: int, hop: int | None = None, offset: int = 0):
     one_d = x.ndim == 1
     x2 = x[None, :] if one_d else x
     n = x2.shape[1]
-    n_frames = 0 if n - offset < n_fft else (n - offset - n_fft) // hop + 1
+    fit = 0 if n - offset < n_fft else (n - offset - n_fft) // hop + 1
+    n_frames = fit if n_frames is None else min(int(n_frames), fit)
     w = hann_symmetric(n_fft)
     out = np.empty((x2.shape[0], n_frames, n_fft // 2 + 1))
     for c in range(x2.shape[0]):
@@ -311,11 +312,12 @@ def frame_magnitudes(x, n_fft: int, hop: int | None = None, offset: int = 0):
 # --------------------------------------------------------------------------
 # The app's cascade (app.py:161-167, :202-205) on one signal
 # --------------------------------------------------------------------------
-def chain(x, fs, M, L, gains, n_fft=4096):
-    """SRC -> EQ -> framed magnitude spectra of z."""
+def chain(x, fs, M, L, gains, n_fft=4096, n_frames=None):
+    """SRC -> EQ -> framed magnitude spectra of z; n_frames limits the spectra to the
+    first frames (the recursive FFT costs ~60 ms per 4096-point frame)."""
     y, fs2 = resample_closed_form(x, fs, M, L)
     z = equalizer(y, fs2, gains)
-    return y, z, frame_magnitudes(z, n_fft), fs2
+    return y, z, frame_magnitudes(z, n_fft, n_frames=n_frames), fs2
 
 
 # --------------------------------------------------------------------------
@@ -340,10 +342,18 @@ def spectrum_db(mag):
     return 20 * np.log10(np.asarray(mag) + 1e-12)
 
 
+def spectrum_db_masked(f, mag):
+    """app.py:207-208: mask = f > 0.5 (drops the DC bin of any practical frame), dB of the bins that pass."""
+    f = np.asarray(f)
+    mask = f > 0.5
+    return mask, 20 * np.log10(np.asarray(mag)[mask] + 1e-12)
+
+
 def pcm16_export(z):
     """app.py:349-354: nan_to_num, divide by the peak when it is > 0, * 32767,
-    truncate to int16.  (Inline code of the Streamlit script, which cannot be
-    imported here: parity for this helper is unpinned.)"""
+    truncate to int16.  Inline code of the Streamlit script, which cannot be
+    imported here; pinned by tests/golden/app_helpers.npz, which make_golden.py
+    produces by executing those statements lifted from app.py with ``ast``."""
     y = np.nan_to_num(np.asarray(z))
     peak = np.max(np.abs(y)) if y.size else 0
     if peak > 0:

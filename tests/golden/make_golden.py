@@ -31,6 +31,60 @@ def gains_dict(values, keys=BANDS):
     return {k: v for k, v in zip(keys, values)}
 
 
+def extract_app_helpers(app_path="/root/reference/app.py"):
+    """The two pieces of arithmetic app.py applies to the kernels' outputs are inline statements of a Streamlit script
+    that cannot be imported (streamlit/plotly absent).  They are pinned by EXECUTING the reference's own statements:
+    the script is parsed with ``ast``, the assignments that compute ``mask_in``/``db_in`` (app.py:207-208) and
+    ``y_final_audio``/``peak`` plus the int16 expression handed to ``write`` (app.py:349-354) are lifted out unchanged
+    and compiled.  Returns (spectrum_db_masked(f, mag) -> (mask, db), pcm16(z) -> int16, {name: line})."""
+    import ast
+
+    tree = ast.parse(open(app_path, encoding="utf-8").read(), filename=app_path)
+    found = {}
+
+    def assigns_to(node, name):
+        return (isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name)
+                and node.targets[0].id == name)
+
+    for node in ast.walk(tree):
+        for name in ("mask_in", "db_in", "y_final_audio", "peak"):
+            if assigns_to(node, name) and name not in found:
+                found[name] = node
+        if isinstance(node, ast.If) and isinstance(node.test, ast.Compare) and isinstance(node.test.left, ast.Name) \
+                and node.test.left.id == "peak" and "peak_if" not in found:
+            found["peak_if"] = node
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id == "write" \
+                and len(node.args) == 3 and "int16_expr" not in found:
+            found["int16_expr"] = node.args[2]
+    missing = {"mask_in", "db_in", "y_final_audio", "peak", "peak_if", "int16_expr"} - set(found)
+    if missing:
+        raise RuntimeError(f"app.py no longer holds {sorted(missing)}")
+    lines = {k: int(v.lineno) for k, v in found.items()}
+
+    def module(*nodes):
+        m = ast.Module(body=list(nodes), type_ignores=[])
+        ast.fix_missing_locations(m)
+        return compile(m, app_path, "exec")
+
+    db_code = module(found["mask_in"], found["db_in"])
+    pcm_code = module(found["y_final_audio"], found["peak"], found["peak_if"])
+    expr = ast.Expression(body=found["int16_expr"])
+    ast.fix_missing_locations(expr)
+    pcm_expr = compile(expr, app_path, "eval")
+
+    def spectrum_db_masked(f, mag):
+        ns = {"np": np, "f_in": f, "mag_in": mag}
+        exec(db_code, ns)
+        return ns["mask_in"], ns["db_in"]
+
+    def pcm16(z):
+        ns = {"np": np, "z_final": z}
+        exec(pcm_code, ns)
+        return eval(pcm_expr, ns)
+
+    return spectrum_db_masked, pcm16, lines
+
+
 def main():
     import scipy
 
@@ -165,9 +219,12 @@ def main():
     spec["valueerror_lens"] = np.array(err_lens)
     np.savez_compressed(os.path.join(HERE, "spectrum.npz"), **spec)
 
-    # ---------------- C1 stand-in chain ----------------------
+    # ---------------- C1 stand-in chain: 1 channel x 30 s @ 44.1 kHz ----------------
+    # x is not stored (5 MB of noise): it is default_rng(20261018).uniform(-1, 1, 30 * 44100) -> float32 ->
+    # peak-normalised as the loader does (dsp_core.py:26-31); x_check pins the generator's stream.
+    n_c1 = 30 * 44100
     rng = np.random.default_rng(20261018)
-    x = rng.uniform(-1, 1, 44100).astype(np.float32)        # 1 s stand-in (30 s in the bench)
+    x = rng.uniform(-1, 1, n_c1).astype(np.float32)
     peak = np.max(np.abs(x))
     x = x / peak                                             # loader's normalisation, dsp_core.py:29-31
     y, fs2 = ref.conversion_tasa_muestreo(x, 44100, 2, 3)
@@ -177,10 +234,44 @@ def main():
     w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(4096) / 4095)
     mag = np.abs(ref.fft_diezmado_en_tiempo(frame * w))[:2049]
     f3, m3 = ref.calcular_espectro_magnitud(z[:100000], fs2)
-    np.savez_compressed(os.path.join(HERE, "chain_c1.npz"), x=x,
-                        y_head=y[:4096], y_tail=y[-4096:], z_head=z[:4096], z_tail=z[-4096:],
+    # 4096-point frames every 2^17 samples: what the batched chain's framed spectra are compared with
+    frame_starts = np.arange(0, len(z) - 4096 + 1, 1 << 17)
+    frames_mag = np.stack([np.abs(ref.fft_diezmado_en_tiempo(z[s0:s0 + 4096] * w))[:2049] for s0 in frame_starts])
+    np.savez_compressed(os.path.join(HERE, "chain_c1.npz"), n=np.array(n_c1), seed=np.array(20261018),
+                        x_check=np.array([float(np.sum(x.astype(np.float64))), float(x[0]), float(x[-1])]),
+                        y_head=y[:4096], y_tail=y[-4096:], y_mid=y[mid:mid + 4096],
+                        z_head=z[:4096], z_tail=z[-4096:], z_mid=z[mid:mid + 4096],
+                        y_sum=np.array([np.sum(y), np.sum(np.abs(y)), np.sum(y * y)]),
                         z_sum=np.array([np.sum(z), np.sum(np.abs(z)), np.sum(z * z)]),
-                        mag4096=mag, f_app=f3, m_app=m3, fs2=np.array(fs2))
+                        mag4096=mag, f_app=f3, m_app=m3, fs2=np.array(fs2),
+                        frame_starts=frame_starts, frames_mag=frames_mag)
+
+    # ---------------- what app.py does to the kernels' outputs (app.py:207-210, :349-354) ----------------
+    # executed from the reference's own statements (extract_app_helpers), on the C1 spectrum and on edge inputs
+    db_masked, pcm16, app_lines = extract_app_helpers()
+    helpers = {"app_lines": np.array([app_lines[k] for k in sorted(app_lines)]),
+               "app_line_names": np.array(sorted(app_lines))}
+    mask, db = db_masked(f3, m3)
+    helpers["f_c1"], helpers["m_c1"], helpers["mask_c1"], helpers["db_c1"] = f3, m3, mask, db
+    rng = np.random.default_rng(6)
+    m_edge = np.concatenate([[0.0, 1e-13, 1e-12, 1.0, 1e6], rng.uniform(0, 40, 251)])
+    f_edge = np.concatenate([[0.0, 0.25, 0.5, 0.5000001, 23.4], np.arange(251) * 23.4375 + 46.875])
+    mask, db = db_masked(f_edge, m_edge)
+    helpers["f_edge"], helpers["m_edge"], helpers["mask_edge"], helpers["db_edge"] = f_edge, m_edge, mask, db
+    zs = {
+        "c1": z[:48000].copy(),
+        "noise": rng.uniform(-0.8, 0.8, 30011),
+        "nan_inf": np.concatenate([rng.uniform(-0.3, 0.3, 500), [np.nan, 0.7, -0.9]]),
+        "zeros": np.zeros(257),
+        "f32": rng.uniform(-0.5, 0.5, 4099).astype(np.float32),
+        "full": np.array([1.0, -1.0, 0.5, -0.5, 0.999969482421875, 1.0 / 32767, 0.5 / 32767]),
+    }
+    with np.errstate(all="ignore"):
+        for name, zz in zs.items():
+            helpers[f"z_{name}"] = zz.copy()
+            helpers[f"pcm_{name}"] = pcm16(zz.copy())
+    helpers["pcm_names"] = np.array(sorted(zs))
+    np.savez_compressed(os.path.join(HERE, "app_helpers.npz"), **helpers)
 
     # ---------------- loader front end (dsp_core.py:10-35) ------------------
     # the real cargar_senal_audio, fed through a stand-in soundfile.read

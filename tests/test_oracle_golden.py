@@ -116,7 +116,7 @@ def test_spectrum(golden_spectrum):
 def test_chain_c1(golden_chain):
     g = golden_chain
     x = g["x"]
-    y, z, mags, fs2 = o.chain(x, 44100, 2, 3, gains_dict((6, -3, 4, -6, 3, -9)), n_fft=4096)
+    y, z, mags, fs2 = o.chain(x, 44100, 2, 3, gains_dict((6, -3, 4, -6, 3, -9)), n_fft=4096, n_frames=2)
     assert fs2 == int(g["fs2"])
     assert np.max(np.abs(y[:4096] - g["y_head"])) <= 1e-13
     assert np.max(np.abs(y[-4096:] - g["y_tail"])) <= 1e-13
@@ -124,9 +124,16 @@ def test_chain_c1(golden_chain):
     assert np.max(np.abs(z[-4096:] - g["z_tail"])) <= 1e-12
     sums = np.array([np.sum(z), np.sum(np.abs(z)), np.sum(z * z)])
     assert np.allclose(sums, g["z_sum"], rtol=1e-11)
+    assert np.allclose([np.sum(y), np.sum(np.abs(y)), np.sum(y * y)], g["y_sum"], rtol=1e-11)
     mid = len(z) // 2
+    assert len(x) == 30 * 44100 and len(z) == 45 * 44100          # C1 is 30 s
+    assert np.max(np.abs(y[mid:mid + 4096] - g["y_mid"])) <= 1e-13
+    assert np.max(np.abs(z[mid:mid + 4096] - g["z_mid"])) <= 1e-12
     frame = o.frame_magnitudes(z, 4096, offset=mid)[0]
     assert o.rel_err(frame, g["mag4096"]) <= 1e-10
+    for s0, ref_mag in zip(g["frame_starts"], g["frames_mag"]):
+        assert o.rel_err(o.frame_magnitudes(z, 4096, offset=int(s0), n_frames=1)[0], ref_mag) <= 1e-10
+    assert o.rel_err(mags[0], g["frames_mag"][0]) <= 1e-10
     f, m = o.magnitude_spectrum(z[:100000], fs2)
     assert o.rel_err(m, g["m_app"]) <= 1e-10 and np.allclose(f, g["f_app"])
 
@@ -155,6 +162,23 @@ def test_loader_front_end_matches_reference():
     for name in ("stereo", "mono", "quad", "tiny", "silence"):
         out = o.load_mono_normalize(g[f"in_{name}"])
         assert out.dtype == np.float32 and np.array_equal(out, g[f"out_{name}"]), name
+
+
+def test_app_helpers_pinned_by_the_reference_statements(golden_app):
+    """app.py:207-208 (f > 0.5 mask, 20 log10(mag + 1e-12)) and app.py:349-354 (nan_to_num, peak normalise, * 32767,
+    int16) as executed from the reference's own statements by tests/golden/make_golden.py (ast extraction)."""
+    g = golden_app
+    assert dict(zip(g["app_line_names"].tolist(), g["app_lines"].tolist())) == {
+        "mask_in": 207, "db_in": 208, "y_final_audio": 349, "peak": 350, "peak_if": 351, "int16_expr": 354}
+    for tag in ("c1", "edge"):
+        mask, db = o.spectrum_db_masked(g[f"f_{tag}"], g[f"m_{tag}"])
+        assert np.array_equal(mask, g[f"mask_{tag}"])
+        assert np.array_equal(db, g[f"db_{tag}"])
+        assert np.array_equal(o.spectrum_db(g[f"m_{tag}"])[mask], g[f"db_{tag}"])
+    for name in g["pcm_names"].tolist():
+        with np.errstate(all="ignore"):
+            out = o.pcm16_export(g[f"z_{name}"])
+        assert out.dtype == np.int16 and np.array_equal(out, g[f"pcm_{name}"]), name
 
 
 def test_export_helpers_known_answers():
