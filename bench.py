@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-f64", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the side-stream spectra all-gather measurement")
+    ap.add_argument("--gather-clips", type=int, default=1024, help="clips per rank whose spectra the gather leg exchanges")
     return ap.parse_args()
 
 
@@ -566,6 +568,44 @@ def run_b200(args):
                                            "against": "oracle pcm16_export of the float32 z the plain call returned"}
         del dq
 
+    # ---- the optional exchange: all-gather of per-clip spectra over NCCL on a side stream, alone and
+    # overlapped with the next waves' kernels.  Not part of `value`: the data path has no collective.
+    gather_line = None
+    if world > 1 and not args.no_gather and args.workload == "chain":
+        gc = max(1, min(args.gather_clips, clips))
+        snap = mag[:gc].clone()
+        g = shard.SpectraGather(world * gc)
+        for _ in range(2):
+            g.start(snap).wait()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g_steps = max(1, min(args.steps, 5))
+        g0.record()
+        for _ in range(g_steps):
+            g.start(snap).wait()
+        g1.record()
+        barrier()
+        alone_ms = g0.elapsed_time(g1) / g_steps
+        barrier()
+        g0.record()
+        for _ in range(g_steps):
+            step_chain()
+            g.wait()
+            g.start(snap)
+        g.wait()
+        g1.record()
+        barrier()
+        with_ms = g0.elapsed_time(g1) / g_steps
+        tg = torch.tensor([alone_ms, with_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        nbytes = snap.numel() * snap.element_size()
+        gather_line = {"collective": "all_gather_into_tensor (NCCL) on a side stream, shard.SpectraGather",
+                       "clips_per_rank": gc, "bytes_per_rank": nbytes, "alone_ms": float(tg[0].item()),
+                       "busbw_gbs": nbytes * (world - 1) / (float(tg[0].item()) * 1e-3) / 1e9,
+                       "chain_step_ms_with_gather_overlapped": float(tg[1].item()),
+                       "chain_step_ms": ms_max / args.steps}
+        del snap, g
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         alg_bytes = {
@@ -617,6 +657,8 @@ def run_b200(args):
             line["f64"] = f64_line
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
+        if gather_line is not None:
+            line["gather"] = gather_line
         emit(line)
     if world > 1:
         dist.destroy_process_group()

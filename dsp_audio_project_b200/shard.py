@@ -44,3 +44,70 @@ def gather_spectra(local, n_channels: int, group=None):
     out = local.new_empty((world * per,) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(out, local, group=group)
     return out[:n_channels]
+
+
+class SpectraGather:
+    """The optional exchange of SURVEY.md 8e off the data path: the all-gather of a wave's spectra runs on a side
+    stream, so the next wave's kernels (main stream) overlap the NVLink transfer.
+
+        g = SpectraGather(n_channels)           # once; n_channels = clips of a wave over ALL ranks
+        chain.run(x, z=z, mag=mag)              # wave k on the current stream
+        g.start(mag)                            # returns at once; the collective waits for wave k on the device
+        chain.run(x2, z=z2, mag=mag2)           # wave k+1 overlaps the gather
+        full = g.wait()                         # [n_channels, frames, bins] on every rank, current stream ordered after it
+
+    ``mag`` must not be overwritten before wait() (use two spectra buffers, as above).  NCCL on GPUs; with the gloo
+    backend (CPU tests) the same calls run synchronously."""
+
+    def __init__(self, n_channels: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.n_channels = int(n_channels)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.per = -(-self.n_channels // self.world) if self.n_channels else 0
+        self._cuda = torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+        self._side = torch.cuda.Stream() if self._cuda else None
+        self._out = None
+        self._pad = None
+        self._done = None
+
+    def start(self, local):
+        import torch
+        import torch.distributed as dist
+
+        if local.shape[0] > self.per:
+            raise ValueError("local block larger than ceil(n_channels / world)")
+        shape = (self.world * self.per,) + tuple(local.shape[1:])
+        if self._out is None or tuple(self._out.shape) != shape or self._out.dtype != local.dtype:
+            self._out = local.new_empty(shape)
+        if not self._cuda:
+            src = local
+            if local.shape[0] < self.per:
+                src = torch.cat([local, local.new_zeros((self.per - local.shape[0],) + tuple(local.shape[1:]))], dim=0)
+            dist.all_gather_into_tensor(self._out, src.contiguous(), group=self.group)
+            return self
+        ready = torch.cuda.Event()
+        ready.record()                                   # wave k's kernels, on the caller's stream
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            src = local
+            if local.shape[0] < self.per:                # the last rank may own fewer clips: pad on the side stream
+                if self._pad is None or tuple(self._pad.shape) != (self.per,) + tuple(local.shape[1:]):
+                    self._pad = local.new_zeros((self.per,) + tuple(local.shape[1:]))
+                self._pad[:local.shape[0]].copy_(local, non_blocking=True)
+                src = self._pad
+            local.record_stream(self._side)
+            dist.all_gather_into_tensor(self._out, src.contiguous(), group=self.group)
+            self._done = torch.cuda.Event()
+            self._done.record()
+        return self
+
+    def wait(self):
+        import torch
+
+        if self._cuda and self._done is not None:
+            torch.cuda.current_stream().wait_event(self._done)
+            self._done = None
+        return self._out[:self.n_channels]

@@ -42,6 +42,9 @@ def _worker(rank, world, port, n_channels, out_dir):
         c = torch.arange(start, stop, dtype=torch.float32).view(-1, 1, 1)
         local = c * 100 + torch.arange(3).view(1, 3, 1) * 10 + torch.arange(5).view(1, 1, 5)
         full = gather_spectra(local, n_channels)
+        from dsp_audio_project_b200.shard import SpectraGather
+        g = SpectraGather(n_channels)
+        assert torch.equal(g.start(local).wait(), full)          # the side-stream form (synchronous under gloo)
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), full.numpy())
     finally:
         dist.destroy_process_group()
