@@ -722,31 +722,27 @@ __host__ __device__ __forceinline__ constexpr int fs_row_base(int slot) {
   return slot * kFsRowPitch + ((slot & 1) << 3) + ((slot & 15) >> 1);
 }
 
-template <typename T, int N1>
-__global__ void __launch_bounds__(N1)
-fft4_cols_kernel(const FftArgs<T> a, const FourStep<T> fs) {
+// Workspace accesses of the fused form go to L2 (.cg): the slot of a cluster is rewritten for every transform by
+// other SMs, so a line left in this SM's L1 by the previous transform would be stale.
+template <bool kCg, typename C> __device__ __forceinline__ C ws_load(const C* p) {
+  if constexpr (kCg) return __ldcg(p); else return *p;
+}
+template <bool kCg, typename C> __device__ __forceinline__ void ws_store(C* p, C v) {
+  if constexpr (kCg) __stcg(p, v); else *p = v;
+}
+
+// Columns [16 tile, 16 tile + 16) of transform f: N1-point transforms along n1, times W_nc^(n2 k1), into wsf[k1][n2].
+// N1 threads.  s: kFsTile * PITCH points (the caller keeps other users of it away until the call returns and
+// synchronises before the next use).
+template <typename T, int N1, bool kCg>
+__device__ __forceinline__ void fs_cols_tile(const FftArgs<T>& a, const FourStep<T>& fs, typename Cpx<T>::type* s,
+                                             const typename Cpx<T>::type* s_hi, const typename Cpx<T>::type* s_lo,
+                                             const typename Cpx<T>::type* tw_cols, const long long f, const int tile,
+                                             typename Cpx<T>::type* wsf, const int t) {
   typedef typename Cpx<T>::type C;
   constexpr int Q = N1 / 16, NC = N1 * kFsCols, PITCH = fs_pitch<N1>();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  C* s = reinterpret_cast<C*>(smem_raw);
-  C* s_hi = s + kFsTile * PITCH;
-  C* s_lo = s_hi + NC / 256;
-  // measured on C4: the pass twiddles are faster from shared memory in fp64 (1.94 vs 2.18 ms)
-  // and from global/L1 in fp32 (1.65 vs 1.80 ms)
-  constexpr bool kTwSmem = sizeof(T) == 8;
-  C* s_tw = s_lo + 256;
-  const int t = threadIdx.x;
   const int c = t % kFsTile, tp = t / kFsTile;
-  for (int i = t; i < NC / 256; i += N1) s_hi[i] = fs.tw_hi[i];
-  for (int i = t; i < 256; i += N1) s_lo[i] = fs.tw_lo[i];
-  if constexpr (kTwSmem) {
-    for (int i = t; i < fs.tw_cols_total; i += N1) s_tw[i] = fs.tw_cols[i];
-    __syncthreads();
-  }
-  constexpr int TILES = kFsCols / kFsTile;
-  const long long fl = blockIdx.x / TILES;
-  const int n2 = static_cast<int>(blockIdx.x - fl * TILES) * kFsTile + c;
-  const long long f = a.first + fl;
+  const int n2 = tile * kFsTile + c;
   const long long ch = f / a.n_frames;
   const long long fr = f - ch * a.n_frames;
   const long long fstart = a.offset + fr * a.hop;
@@ -772,7 +768,7 @@ fft4_cols_kernel(const FftArgs<T> a, const FourStep<T> fs) {
     for (int u = 0; u < 16; ++u) tmp[u] = pmul(tmp[u], wp[u * Q * kFsCols]);
   }
   C* sc = s + c * PITCH;
-  ct_passes<T, N1, 0, 1>(tmp, sc, kTwSmem ? s_tw : fs.tw_cols, fs.tw_cols_offset, tp);
+  ct_passes<T, N1, 0, 1>(tmp, sc, tw_cols, fs.tw_cols_offset, tp);
   // W_nc^(n2 k1), k1 = tp + u Q:  W^(n2 tp) * (W^(n2 Q))^u.  Two table products give the base and
   // the step; the powers of the step come from a product tree (<= 4 roundings deep) instead of
   // sixteen scattered table reads per thread, which were the busiest user of the load/store pipe.
@@ -785,53 +781,43 @@ fft4_cols_kernel(const FftArgs<T> a, const FourStep<T> fs) {
   pw[8] = cmul(pw[4], pw[4]);
 #pragma unroll
   for (int u = 9; u < 16; ++u) pw[u] = cmul(pw[8], pw[u - 8]);
-  C* o = fs.ws + fl * NC + n2;
+  C* o = wsf + n2;
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const int k1 = tp + u * Q;
     const C w = u == 0 ? wb : cmul(wb, pw[u]);
-    o[static_cast<long long>(k1) * kFsCols] = cmul(sc[padded(k1)], w);
+    ws_store<kCg>(o + static_cast<long long>(k1) * kFsCols, cmul(sc[padded(k1)], w));
   }
 }
 
-template <typename T, int N1>
-__global__ void __launch_bounds__(256)
-fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
+// Rows of group g of transform f (256 threads, 32 row slots): the 16 primary rows k1 = 16 g + 1 .. 16 g + 16
+// and their mirrors N1 - k1, 128-point transforms along n2, real split, |X| out.  Row N1/2 (the last primary row
+// of the last group) is its own mirror, so its mirror slot carries row 0 -- which pairs with itself too -- instead.
+template <typename T, int N1, bool kCg>
+__device__ __forceinline__ void fs_rows_group(const FftArgs<T>& a, const FourStep<T>& fs, typename Cpx<T>::type* s,
+                                              const typename Cpx<T>::type* s_tw, const long long f, const int g,
+                                              const typename Cpx<T>::type* wsf, const int t) {
   typedef typename Cpx<T>::type C;
   constexpr int M = kFsCols, Q = M / 16, NC = N1 * M;
-  constexpr int G = N1 / 2 / kFsTile;     // groups of 16 primary rows k1 in [1, N1/2]; block G of a frame is row 0
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  C* s = reinterpret_cast<C*>(smem_raw);
-  C* s_tw = s + 2 * kFsTile * kFsRowPitch;
-  const int t = threadIdx.x;
+  constexpr int G = N1 / 2 / kFsTile;     // groups of 16 primary rows k1 in [1, N1/2]
   const int tp = t % Q, slot = t / Q;     // 32 row slots: 0..15 primary rows, 16..31 their mirrors (ascending)
-  for (int i = t; i < fs.tw_rows_total; i += 256) s_tw[i] = fs.tw_rows[i];
-  const long long fl = blockIdx.x / (G + 1);
-  const int g = static_cast<int>(blockIdx.x - fl * (G + 1));
-  const long long f = a.first + fl;
-  int row = -1;
-  if (g < G) row = slot < kFsTile ? (kFsTile * g + 1 + slot) : (N1 - kFsTile * g - 2 * kFsTile + slot);
-  else if (slot == 0) row = 0;
+  const bool last = g == G - 1;
+  int row = slot < kFsTile ? (kFsTile * g + 1 + slot) : (N1 - kFsTile * g - 2 * kFsTile + slot);
+  if (last && slot == kFsTile) row = 0;
   C tmp[16];
-  if (row >= 0) {
-    const C* wp = fs.ws + fl * NC + static_cast<long long>(row) * M + tp;
+  {
+    const C* wp = wsf + static_cast<long long>(row) * M + tp;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) tmp[u] = wp[u * Q];
-  } else {
-#pragma unroll
-    for (int u = 0; u < 16; ++u) { tmp[u].x = T(0); tmp[u].y = T(0); }
+    for (int u = 0; u < 16; ++u) tmp[u] = ws_load<kCg>(wp + u * Q);
   }
   // the real-split twiddles of this thread's bins, requested before the passes
   C twp[M / 16];
-  if (g < G) {
-    const int k1 = kFsTile * g + 1 + (t % kFsTile);
+  const int k1 = kFsTile * g + 1 + (t % kFsTile);
 #pragma unroll
-    for (int i = 0; i < M / 16; ++i) {
-      const int idx = k1 + N1 * (t / kFsTile + 16 * i);
-      twp[i] = a.tw_post[idx <= NC / 2 ? idx : NC - idx];
-    }
+  for (int i = 0; i < M / 16; ++i) {
+    const int idx = k1 + N1 * (t / kFsTile + 16 * i);
+    twp[i] = a.tw_post[idx <= NC / 2 ? idx : NC - idx];
   }
-  __syncthreads();               // pass twiddles are in place
   ct_passes<T, M, 0, 1>(tmp, s + fs_row_base(slot), s_tw, fs.tw_rows_offset, tp);
 
   const long long ch = f / a.n_frames;
@@ -847,11 +833,11 @@ fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
     mg[idx] = finish_mag(p.x * p.x + p.y * p.y, a.db);
     mg[NC - idx] = finish_mag(q.x * q.x + q.y * q.y, a.db);
   };
-  if (g < G) {
+  {
     const int j = t % kFsTile;
-    const int k1 = kFsTile * g + 1 + j;
+    const bool self = 2 * k1 == N1;                          // row N1/2: Z[nc - idx] is in the same row
     const C* pa = s + fs_row_base(j);
-    const C* pb = s + fs_row_base(2 * kFsTile - 1 - j);  // row N1 - k1
+    const C* pb = s + fs_row_base(self ? j : 2 * kFsTile - 1 - j);  // row N1 - k1
 #pragma unroll
     for (int i = 0; i < M / 16; ++i) {
       const int k2 = t / kFsTile + 16 * i;
@@ -859,13 +845,110 @@ fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
       const C Bz = pb[padded(M - 1 - k2)];
       const int idx = k1 + N1 * k2;
       if (idx <= NC / 2) {
-        if (2 * k1 != N1 || k2 < M / 2) emit(A, Bz, idx, twp[i]);  // row N1/2 pairs with itself: take each pair once
-      } else if (2 * k1 != N1) {
+        if (!self || k2 < M / 2) emit(A, Bz, idx, twp[i]);   // a self-paired row: take each pair once
+      } else if (!self) {
         emit(Bz, A, NC - idx, twp[i]);
       }
     }
-  } else if (t <= M / 2) {                                 // row 0 pairs with itself, k2 <-> (M - k2) mod M
-    emit(s[padded(t)], s[padded((M - t) & (M - 1))], N1 * t, a.tw_post[N1 * t]);
+  }
+  if (last && t <= M / 2) {                                  // row 0 pairs with itself, k2 <-> (M - k2) mod M
+    const C* r0 = s + fs_row_base(kFsTile);
+    emit(r0[padded(t)], r0[padded((M - t) & (M - 1))], N1 * t, a.tw_post[N1 * t]);
+  }
+}
+
+template <typename T, int N1>
+__global__ void __launch_bounds__(N1)
+fft4_cols_kernel(const FftArgs<T> a, const FourStep<T> fs) {
+  typedef typename Cpx<T>::type C;
+  constexpr int NC = N1 * kFsCols, PITCH = fs_pitch<N1>();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  C* s_hi = s + kFsTile * PITCH;
+  C* s_lo = s_hi + NC / 256;
+  // measured on C4: the pass twiddles are faster from shared memory in fp64 (1.94 vs 2.18 ms)
+  // and from global/L1 in fp32 (1.65 vs 1.80 ms)
+  constexpr bool kTwSmem = sizeof(T) == 8;
+  C* s_tw = s_lo + 256;
+  const int t = threadIdx.x;
+  for (int i = t; i < NC / 256; i += N1) s_hi[i] = fs.tw_hi[i];
+  for (int i = t; i < 256; i += N1) s_lo[i] = fs.tw_lo[i];
+  if constexpr (kTwSmem) {
+    for (int i = t; i < fs.tw_cols_total; i += N1) s_tw[i] = fs.tw_cols[i];
+    __syncthreads();
+  }
+  constexpr int TILES = kFsCols / kFsTile;
+  const long long fl = blockIdx.x / TILES;
+  const int tile = static_cast<int>(blockIdx.x - fl * TILES);
+  fs_cols_tile<T, N1, false>(a, fs, s, s_hi, s_lo, kTwSmem ? s_tw : fs.tw_cols, a.first + fl, tile, fs.ws + fl * NC, t);
+}
+
+template <typename T, int N1>
+__global__ void __launch_bounds__(256)
+fft4_rows_kernel(const FftArgs<T> a, const FourStep<T> fs) {
+  typedef typename Cpx<T>::type C;
+  constexpr int NC = N1 * kFsCols;
+  constexpr int G = N1 / 2 / kFsTile;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  C* s_tw = s + 2 * kFsTile * kFsRowPitch;
+  const int t = threadIdx.x;
+  for (int i = t; i < fs.tw_rows_total; i += 256) s_tw[i] = fs.tw_rows[i];
+  __syncthreads();               // pass twiddles are in place
+  const long long fl = blockIdx.x / G;
+  const int g = static_cast<int>(blockIdx.x - fl * G);
+  fs_rows_group<T, N1, false>(a, fs, s, s_tw, a.first + fl, g, fs.ws + fl * NC, t);
+}
+
+// The two steps in ONE launch with the workspace resident in L2 (C4: 7.4 GB of DRAM traffic for 3.2 GB algorithmic
+// with the two kernels above, whose workspace of a whole launch goes out to HBM and comes back).  A cluster of
+// kFsCluster CTAs of 256 threads walks transforms cluster-stride: each CTA transforms its share of the column tiles
+// into the cluster's own workspace slot (nc points, rewritten for every transform, so its lines stay dirty in L2 and
+// never need to reach DRAM), the cluster synchronises, each CTA transforms its share of the row groups, and the
+// cluster synchronises again before the slot is overwritten.  N1 = 256 only (n_fft = 2^16: 256 threads serve both
+// the N1-thread column step and the 256-thread row step).
+constexpr int kFsCluster = 4;
+template <typename T, int N1>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 2)
+fft4_fused_kernel(const FftArgs<T> a, const FourStep<T> fs, const long long count) {
+  typedef typename Cpx<T>::type C;
+  static_assert(N1 == 256, "the fused four-step form is built for N1 = 256");
+  constexpr int NC = N1 * kFsCols, PITCH = fs_pitch<N1>();
+  constexpr int TILES = kFsCols / kFsTile, G = N1 / 2 / kFsTile;
+  constexpr int kWork = kFsTile * PITCH > 2 * kFsTile * kFsRowPitch ? kFsTile * PITCH : 2 * kFsTile * kFsRowPitch;
+  constexpr bool kTwSmem = sizeof(T) == 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* s = reinterpret_cast<C*>(smem_raw);
+  C* s_hi = s + kWork;
+  C* s_lo = s_hi + NC / 256;
+  C* s_twr = s_lo + 256;
+  C* s_twc = s_twr + fs.tw_rows_total;
+  const int t = threadIdx.x;
+  for (int i = t; i < NC / 256; i += 256) s_hi[i] = fs.tw_hi[i];
+  for (int i = t; i < 256; i += 256) s_lo[i] = fs.tw_lo[i];
+  for (int i = t; i < fs.tw_rows_total; i += 256) s_twr[i] = fs.tw_rows[i];
+  if constexpr (kTwSmem)
+    for (int i = t; i < fs.tw_cols_total; i += 256) s_twc[i] = fs.tw_cols[i];
+  __syncthreads();
+  unsigned rank, n_clusters_x, cluster_x;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(n_clusters_x));
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cluster_x));
+  C* wsf = fs.ws + static_cast<long long>(cluster_x) * NC;
+  for (long long fl = cluster_x; fl < count; fl += n_clusters_x) {
+    const long long f = a.first + fl;
+    for (int tile = static_cast<int>(rank); tile < TILES; tile += kFsCluster) {
+      fs_cols_tile<T, N1, true>(a, fs, s, s_hi, s_lo, kTwSmem ? s_twc : fs.tw_cols, f, tile, wsf, t);
+      __syncthreads();           // the tile's last reads of s are done before the next user writes it
+    }
+    // columns of every CTA of the cluster are in the slot (release / acquire at cluster scope)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    for (int g = static_cast<int>(rank); g < G; g += kFsCluster) {
+      fs_rows_group<T, N1, true>(a, fs, s, s_twr, f, g, wsf, t);
+      __syncthreads();
+    }
+    // every CTA has read its rows: the slot may be overwritten
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
@@ -1235,6 +1318,42 @@ template <typename T, int N1>
 static int launch_four_step(const FftArgs<T>& a, const FourStep<T>& fs, long long cnt, cudaStream_t stream) {
   typedef typename Cpx<T>::type C;
   constexpr int NC = N1 * kFsCols;
+  if constexpr (N1 == 256) {
+    // Opt-in (DSPB200_FFT_FUSED4=1).  Measured on C4 (512 x 2^20 samples, fp32): DRAM traffic 3.38 GB instead of 7.4 GB
+    // (1.05 x algorithmic), but 1.86 ms against 1.57 ms for the two kernels: with three CTAs of 256 threads per SM and
+    // two cluster barriers per transform the SMs issue 37 % of the time and the shared-memory pipe is 64 % busy --
+    // the transforms are bound by the exchanges of the 16-points-per-thread passes, not by HBM.
+    const char* fe = getenv("DSPB200_FFT_FUSED4");
+    if (fe != nullptr && atoi(fe) != 0) {
+      constexpr int kWork = kFsTile * fs_pitch<N1>() > 2 * kFsTile * kFsRowPitch ? kFsTile * fs_pitch<N1>() : 2 * kFsTile * kFsRowPitch;
+      const size_t smem = (static_cast<size_t>(kWork) + NC / 256 + 256 + fs.tw_rows_total +
+                           (sizeof(T) == 8 ? fs.tw_cols_total : 0)) * sizeof(C);
+      auto kf = fft4_fused_kernel<T, N1>;
+      DSP_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kFsCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3(kFsCluster, 1, 1);
+      int max_clusters = 0;
+      DSP_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kf, &cfg));
+      if (max_clusters < 1) max_clusters = 1;
+      if (const char* ev = getenv("DSPB200_FFT_FUSED4_CLUSTERS")) {
+        const int lim = atoi(ev);
+        if (lim >= 1 && lim < max_clusters) max_clusters = lim;
+      }
+      const long long n_clusters = cnt < max_clusters ? cnt : max_clusters;
+      cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * kFsCluster), 1, 1);
+      if (getenv("DSPB200_FFT_TRACE")) fprintf(stderr, "fft4_fused N1=%d smem=%zu clusters=%lld (max %d)\n", N1, smem, n_clusters, max_clusters);
+      DSP_CUDA(cudaLaunchKernelEx(&cfg, kf, a, fs, cnt));
+      return after_launch("fft4_fused_kernel");
+    }
+  }
   const size_t smem1 = (static_cast<size_t>(kFsTile) * fs_pitch<N1>() + NC / 256 + 256 +
                         (sizeof(T) == 8 ? fs.tw_cols_total : 0)) * sizeof(C);
   const size_t smem2 = (static_cast<size_t>(2 * kFsTile) * kFsRowPitch + fs.tw_rows_total) * sizeof(C);
@@ -1242,7 +1361,7 @@ static int launch_four_step(const FftArgs<T>& a, const FourStep<T>& fs, long lon
   auto k2 = fft4_rows_kernel<T, N1>;
   DSP_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem1)));
   DSP_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-  const long long b1 = cnt * (kFsCols / kFsTile), b2 = cnt * (N1 / 2 / kFsTile + 1);
+  const long long b1 = cnt * (kFsCols / kFsTile), b2 = cnt * (N1 / 2 / kFsTile);
   DSP_CHECK(b1 < (1LL << 31) && b2 < (1LL << 31), "too many transforms in one launch");
   k1<<<static_cast<unsigned>(b1), N1, smem1, stream>>>(a, fs);
   DSP_TRY(after_launch("fft4_cols_kernel"));

@@ -278,15 +278,18 @@ __global__ void __launch_bounds__(256)
 generate_uniform_kernel(T* __restrict__ x, long long stride, long long channels, long long n, long long first_channel,
                         unsigned long long seed, T lo, T span) {
   const long long quads = (n + 3) / 4;
+  const unsigned long long pairs_per_row = static_cast<unsigned long long>((n + 1) / 2);
   for (long long c = blockIdx.y; c < channels; c += gridDim.y) {
     T* row = x + c * stride;
-    const unsigned long long base = static_cast<unsigned long long>(first_channel + c) * static_cast<unsigned long long>(n);
+    // one 64-bit hash per PAIR of samples (two 64-bit multiplies each: per sample they were as long as the store)
+    const unsigned long long base = static_cast<unsigned long long>(first_channel + c) * pairs_per_row;
     for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < quads; q += static_cast<long long>(gridDim.x) * blockDim.x) {
       T v[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned long long h = splitmix64(seed + 0x9E3779B97F4A7C15ull * (base + static_cast<unsigned long long>(4 * q + e) + 1ull));
-        v[e] = affine_rn(lo, span, static_cast<T>(static_cast<unsigned>(h >> 40)) * static_cast<T>(1.0 / 16777216.0));
+      for (int e = 0; e < 2; ++e) {
+        const unsigned long long h = splitmix64(seed + 0x9E3779B97F4A7C15ull * (base + static_cast<unsigned long long>(2 * q + e) + 1ull));
+        v[2 * e] = affine_rn(lo, span, static_cast<T>(static_cast<unsigned>(h >> 40)) * static_cast<T>(1.0 / 16777216.0));
+        v[2 * e + 1] = affine_rn(lo, span, static_cast<T>(static_cast<unsigned>(h & 0xffffffffull) >> 8) * static_cast<T>(1.0 / 16777216.0));
       }
       if (4 * q + 3 < n && (reinterpret_cast<uintptr_t>(row + 4 * q) % (4 * sizeof(T))) == 0) {
         if (sizeof(T) == 4) {

@@ -289,8 +289,9 @@ int dspb200_mono_normalize_run_f32(const float* in, int64_t clips, int64_t frame
                                    int64_t mono_stride, float* peaks, void* stream);
 
 /* Synthetic clips for the throughput configurations (inputs are
- * generated on the device wave by wave).  x[c, i] = lo + (hi - lo) * u with
- * u = (splitmix64(seed + 0x9E3779B97F4A7C15 * ((first_channel + c) * n + i + 1)) >> 40) / 2^24:
+ * generated on the device wave by wave).  x[c, i] = lo + (hi - lo) * u / 2^24 with
+ * h = splitmix64(seed + 0x9E3779B97F4A7C15 * ((first_channel + c) * ceil(n / 2) + i / 2 + 1)) and
+ * u = h >> 40 for even i, (h & 0xffffffff) >> 8 for odd i (one hash per pair of samples):
  * counter based, reproducible on the host. */
 int dspb200_generate_uniform_f32(float* x, int64_t stride, int64_t channels, int64_t n, int64_t first_channel,
                                  uint64_t seed, double lo, double hi, void* stream);

@@ -364,17 +364,21 @@ def pcm16_export(z):
 def synthetic_clips(channels: int, n: int, seed: int, lo: float = -0.5, hi: float = 0.5, first_channel: int = 0,
                           dtype=np.float32):
     """numpy restatement of the library's on-device clip generator (dspb200_generate_uniform_*, csrc/post.cu: splitmix64
-    of a per-sample counter, top 24 bits): not reference behaviour, only how the throughput configurations of
+    of a per-pair counter, 24 bits per sample): not reference behaviour, only how the throughput configurations of
     SURVEY.md 8d make their inputs, so that the tests can reproduce a device-generated wave on the host."""
-    idx = (np.arange(first_channel, first_channel + channels, dtype=np.uint64)[:, None] * np.uint64(n)
-           + np.arange(1, n + 1, dtype=np.uint64)[None, :])
+    pairs = (n + 1) // 2
+    idx = (np.arange(first_channel, first_channel + channels, dtype=np.uint64)[:, None] * np.uint64(pairs)
+           + np.arange(1, pairs + 1, dtype=np.uint64)[None, :])
     with np.errstate(over="ignore"):
         z = np.uint64(int(seed) & (2 ** 64 - 1)) + np.uint64(0x9E3779B97F4A7C15) * idx
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
     dt = np.dtype(dtype)
-    u = (z >> np.uint64(40)).astype(dt) * dt.type(1.0 / 16777216.0)
+    bits = np.empty((channels, 2 * pairs), dtype=np.uint64)
+    bits[:, 0::2] = z >> np.uint64(40)                                   # even samples: top 24 bits
+    bits[:, 1::2] = (z & np.uint64(0xFFFFFFFF)) >> np.uint64(8)          # odd samples: top 24 bits of the low word
+    u = bits[:, :n].astype(dt) * dt.type(1.0 / 16777216.0)
     return (dt.type(lo) + dt.type(hi - lo) * u).astype(dt)
 
 

@@ -890,3 +890,22 @@ def test_wrong_plan_handles_are_rejected(pk, torch_cuda):
 def test_library_reports_launches(pk):
     from dsp_audio_project_b200 import _lib
     assert _lib.launch_count() > 0
+
+
+def test_long_fft_fused_four_step_form_matches(pk, torch_cuda, monkeypatch):
+    """The opt-in single-launch form of the 2^16-point transform (DSPB200_FFT_FUSED4=1: clusters of four CTAs keep the
+    four-step workspace in L2) gives the same spectra as the default two-kernel form, ragged tail included."""
+    torch = torch_cuda
+    rng = np.random.default_rng(65)
+    for dt, tol in ((np.float32, TOL_F32_FFT), (np.float64, TOL_F64)):
+        x = torch.as_tensor(rng.uniform(-1, 1, (5, 3 * 65536 + 1000)).astype(dt), device="cuda")
+        plan = pk.FftPlan(65536, dt, hann=True)
+        monkeypatch.delenv("DSPB200_FFT_FUSED4", raising=False)
+        ref = plan.magnitudes(x, n_frames=4, n_valid=3 * 65536 + 1000).clone()     # the 4th frame is zero padded
+        monkeypatch.setenv("DSPB200_FFT_FUSED4", "1")
+        got = plan.magnitudes(x, n_frames=4, n_valid=3 * 65536 + 1000)
+        monkeypatch.delenv("DSPB200_FFT_FUSED4", raising=False)
+        assert float((got - ref).abs().max() / ref.abs().max()) <= 1e-6 if dt == np.float32 else 1e-14
+        w = o.hann_symmetric(65536)
+        want = np.abs(np.fft.rfft(x[2, 65536:2 * 65536].cpu().numpy().astype(np.float64) * w))
+        assert o.rel_err(got[2, 1].cpu().numpy(), want) <= tol

@@ -135,7 +135,7 @@ def test_chain_host_export_form(env, dt):
     from conftest import gains_dict
     gd = gains_dict((6, -3, 4, -6, 3, -9))
     rng = np.random.default_rng(11)
-    x = rng.uniform(-0.9, 0.9, (37, 9001)).astype(dt)       # 37 clips: two 32-clip slabs, the second ragged
+    x = rng.uniform(-0.9, 0.9, (37, 9008)).astype(dt)       # 37 clips: two 32-clip slabs, the second ragged; n_out = 13512 = 8 k: dense int16 rows
     x[5] = 0.0                                              # a silent clip: peak 0, no division
     lin = pk.Chain(3, 2, 44100, gd, n_fft=1024, dtype=dt)
     dbc = pk.Chain(3, 2, 44100, gd, n_fft=1024, dtype=dt, db=True)
@@ -151,8 +151,35 @@ def test_chain_host_export_form(env, dt):
     big = mag > 1e-4 * mag.max()
     assert np.max(np.abs(db[big] - ref_db[big])) <= (1e-8 if dt == np.float64 else 2e-3)
     # odd row lengths (n_out not a multiple of 8) take the pitched device rows
-    x2 = x[:3, :9000 - 7]
+    x2 = np.ascontiguousarray(x[:3, :9000 - 7])
     z2, _ = lin.run_host(x2)
     q2, _, _ = dbc.run_host_pcm16(x2)
     ref2 = np.stack([o.pcm16_export(z2[c].astype(np.float64) if dt == np.float64 else z2[c]) for c in range(3)])
     assert np.abs(q2.astype(np.int32) - ref2.astype(np.int32)).max() <= (0 if dt == np.float64 else 1)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_generate_uniform_matches_its_numpy_twin(env, dt):
+    """dspb200_generate_uniform_*: the counter-based clip generator of the throughput configurations,
+    bit for bit against oracle.synthetic_clips; a rank's block equals the same rows of the whole batch."""
+    torch, pk = env
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    for n in (1001, 1000, 7, 4096):
+        x = torch.empty((6, n), dtype=tdt, device="cuda")
+        pk.generate_uniform(x, 4, -0.5, 0.5)
+        ref = o.synthetic_clips(6, n, 4, -0.5, 0.5, dtype=dt)
+        assert np.array_equal(x.cpu().numpy(), ref), n
+        part = torch.empty((2, n), dtype=tdt, device="cuda")
+        pk.generate_uniform(part, 4, -0.5, 0.5, first_channel=3)
+        assert np.array_equal(part.cpu().numpy(), ref[3:5]), n
+    # a padded (strided) destination, other bounds
+    buf = torch.full((3, 520), 9.0, dtype=tdt, device="cuda")
+    pk.generate_uniform(buf[:, :513], 77, -1.0, 0.25)
+    ref = o.synthetic_clips(3, 513, 77, -1.0, 0.25, dtype=dt)
+    got = buf.cpu().numpy()
+    assert np.array_equal(got[:, :513], ref) and np.all(got[:, 513:] == 9.0)
+    big = torch.empty((4, 200000), dtype=tdt, device="cuda")
+    pk.generate_uniform(big, 5, -0.5, 0.5)
+    b = big.cpu().numpy().astype(np.float64)
+    assert b.min() >= -0.5 and b.max() < 0.5 and abs(b.mean()) < 2e-3 and abs(b.std() - 0.2887) < 2e-3
+    assert abs(np.corrcoef(b[0, :-1], b[0, 1:])[0, 1]) < 0.01          # the two halves of a hash are independent
