@@ -54,6 +54,7 @@ SIGNATURES = {
     "dspb200_eq_host_f64": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64]),
     "dspb200_eq_plan_kernel_kind": (C.c_int, [c_p, c_i64, c_i64, c_i64, _pi]),
     "dspb200_eq_plan_chunk_system": (C.c_int, [c_p, _pi, _pi, _pd, _pd, _pd]),
+    "dspb200_eq_plan_warm_chunks": (C.c_int, [c_p, C.POINTER(C.c_int)]),
     "dspb200_eq_plan_describe": (C.c_int, [c_p, _pi, _pd, C.c_int]),
     "dspb200_fft_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(c_p)]),
     "dspb200_fft_plan_destroy": (C.c_int, [c_p]),

@@ -854,6 +854,15 @@ int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, i
   return DSPB200_OK;
 }
 
+int dspb200_eq_plan_warm_chunks(const dspb200_eq_plan* plan, int* chunks) {
+  DSP_PLAN(plan, kMagicEq, "eq");
+  DSP_CHECK(chunks != nullptr, "NULL argument");
+  LtiChunkSystem cs;
+  DSP_TRY(lti_chunk_system(plan->sections.data(), static_cast<int>(plan->sections.size()), cs));
+  *chunks = cs.rows > 0 ? lti_warm_chunks(cs) : 0;
+  return DSPB200_OK;
+}
+
 int dspb200_eq_plan_chunk_system(const dspb200_eq_plan* plan, int* rows, int* states, double* tk, double* o,
                                  double* phi) {
   DSP_PLAN(plan, kMagicEq, "eq");

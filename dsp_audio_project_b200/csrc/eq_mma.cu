@@ -86,6 +86,8 @@ struct LtiArgs {
   float* xfer;                  // [n_jobs][kS][128] end states handed to the group's next slice
   float* state;                 // streaming form: [channels][16] state after the block (NULL: not kept)
   int state_in;                 // streaming form: start from `state` instead of zero
+  int warm;                     // > 0: slices are independent; a later slice starts `warm` chunks early from a zero
+                                // state and only stores from its own first chunk on (no hand-over between slices)
   int clip;
   unsigned long long* prof;     // development: cycles per epilogue phase (NULL = off)
   float phi[kLtiMaxStates * kLtiMaxStates];
@@ -158,7 +160,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     mbar_wait(&job_full[i % kJobQ], (i / kJobQ) & 1);
     return *reinterpret_cast<volatile long long*>(&job_q[i % kJobQ]);
   };
-  struct Job { int g, h, t0, t1; };
+  struct Job { int g, h, tw, t0, t1; };   // chunks [tw, t0) are the warm-up of an overlapping slice (tw == t0 otherwise)
   auto job_of = [&](long long j) -> Job {
     Job r;
     const int jj = static_cast<int>(j), ng = static_cast<int>(a.n_groups), cpj = static_cast<int>(a.chunks_per_job);
@@ -166,6 +168,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     r.g = jj - r.h * ng;
     r.t0 = r.h * cpj;
     r.t1 = r.t0 + cpj < static_cast<int>(a.n_tt) ? r.t0 + cpj : static_cast<int>(a.n_tt);
+    r.tw = a.warm > 0 ? (r.t0 > a.warm ? r.t0 - a.warm : 0) : r.t0;
     return r;
   };
 
@@ -189,7 +192,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         mbar_arrive(&job_full[ji % kJobQ]);
         if (j < 0) break;
         const Job jb = job_of(j);
-        for (int tt = jb.t0; tt < jb.t1; ++tt)
+        for (int tt = jb.tw; tt < jb.t1; ++tt)
           for (int kb = 0; kb < kNkb; ++kb, ++it) {
             const int s = it % kXSlots;
             if (it >= kXSlots) mbar_wait(&empty_x[s], ((it / kXSlots) - 1) & 1);
@@ -241,7 +244,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const long long j = next_job(ji);
         if (j < 0) break;
         const Job jb = job_of(j);
-        for (int tt = jb.t0; tt < jb.t1; ++tt, ++ti) {
+        for (int tt = jb.tw; tt < jb.t1; ++tt, ++ti) {
           const int b = ti % kAccs;
           if (ti >= kAccs) mbar_wait(&acc_empty[b], ((ti / kAccs) - 1) & 1);
           tc_fence_after();
@@ -275,7 +278,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const long long j = next_job(ji);
       if (j < 0) break;
       const Job jb = job_of(j);
-      for (int n_kb = (jb.t1 - jb.t0) * kNkb; n_kb > 0; --n_kb, ++it) {
+      for (int n_kb = (jb.t1 - jb.tw) * kNkb; n_kb > 0; --n_kb, ++it) {
           const int s = it % kXSlots;
           mbar_wait(&mid[s], (it / kXSlots) & 1);
           float4* buf = reinterpret_cast<float4*>(x_ptr(s)) + ctid;
@@ -329,10 +332,16 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int g = jb.g;
       float s[kS];
       const long long chan = static_cast<long long>(g) * kTM + warp * 32 + lane;
-      if (jb.h == 0 && !a.state_in) {
+      if (jb.tw == 0 && !a.state_in) {
 #pragma unroll
         for (int i = 0; i < kS; ++i) s[i] = 0.f;     // zero initial state per channel (lfilter, dsp_core.py:214)
-      } else if (jb.h == 0) {
+      } else if (a.warm > 0 && jb.tw > 0) {
+        // overlapping slice: zero state `warm` chunks before its first own chunk; what the true state would add has
+        // decayed below float32 resolution by then (LtiMmaPlan::warm_chunks)
+#pragma unroll
+        for (int i = 0; i < kS; ++i) s[i] = 0.f;
+        hand_over(s);
+      } else if (jb.tw == 0) {
         // streaming form: the state the previous block of these channels ended in
 #pragma unroll
         for (int i = 0; i < kS; ++i) s[i] = chan < a.channels ? __ldcg(a.state + chan * kLtiMaxStates + i) : 0.f;
@@ -347,7 +356,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int i = 0; i < kS; ++i) s[i] = __ldcg(r + i * kTM);
         hand_over(s);
       }
-      for (int tt = jb.t0; tt < jb.t1; ++tt, ++ti) {
+      for (int tt = jb.tw; tt < jb.t1; ++tt, ++ti) {
         const int b = ti % kAccs;
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         const bool prof = a.prof && threadIdx.x == 0;
@@ -378,6 +387,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // clip; each thread lays its channel's 32-sample runs into a 128-byte-swizzled staging tile, which goes out
         // as one TMA store of [128 channels x 32 samples] (full lines, clipped at the tensor's edges by the hardware)
         const int r = warp * 32 + lane;
+        if (tt >= jb.t0)                                      // warm-up chunks of an overlapping slice store nothing
 #pragma unroll
         for (int blk = 0; blk < kRows / 32; ++blk, ++n_st) {
           unsigned char* stage = stage0 + static_cast<size_t>(n_st % kStages) * kXBytes;
@@ -415,7 +425,7 @@ lti_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < kS; ++i) a.state[chan * kLtiMaxStates + i] = s[i];
       }
-      if (jb.t1 < static_cast<int>(a.n_tt)) {
+      if (jb.t1 < static_cast<int>(a.n_tt) && a.warm == 0) {
         // the group goes on in a later slice: leave the end state where that slice will pick it up
         float* r = a.xfer + static_cast<size_t>(job) * (kS * kTM) + warp * 32 + lane;
 #pragma unroll
@@ -559,6 +569,61 @@ int lti_chunk_system(const Section* sec, int ns, LtiChunkSystem& cs, int rows) {
   return DSPB200_OK;
 }
 
+// How many chunks after a start from a ZERO state the output is within 2^-24 of max|x| of the true one (float64,
+// host).  With |x| <= 1 the true state is bounded elementwise by b = sum_k |Phi^k K| 1; what a wrong start state e
+// still contributes w chunks later is O Phi^w e, so the first w with max_r (|O| |Phi^w| b)_r <= 2^-24 is enough
+// (elementwise bounds: conservative by a small factor, i.e. a few hundred samples).  0: no such w within 4096 chunks.
+int lti_warm_chunks(const LtiChunkSystem& cs) {
+  const int n = cs.states, rows = cs.rows, ld = kLtiMaxStates;
+  if (n < 1 || rows < 1) return 0;
+  auto phi_at = [&](int i, int j) { return cs.phi[static_cast<size_t>(i) * ld + j]; };
+  std::vector<double> m(static_cast<size_t>(n) * rows), m2(static_cast<size_t>(n) * rows), b(static_cast<size_t>(n), 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < rows; ++k) m[static_cast<size_t>(i) * rows + k] = cs.tk[static_cast<size_t>(rows + i) * rows + k];
+  bool converged = false;
+  for (int it = 0; it < 8192 && !converged; ++it) {
+    double rmax = 0.0, bmax = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double r = 0.0;
+      for (int k = 0; k < rows; ++k) r += std::fabs(m[static_cast<size_t>(i) * rows + k]);
+      b[static_cast<size_t>(i)] += r;
+      rmax = r > rmax ? r : rmax;
+      bmax = b[static_cast<size_t>(i)] > bmax ? b[static_cast<size_t>(i)] : bmax;
+    }
+    if (!(rmax == rmax) || !std::isfinite(bmax)) return 0;
+    if (rmax <= 1e-13 * bmax) { converged = true; break; }
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < rows; ++k) {
+        double acc = 0.0;
+        for (int j = 0; j < n; ++j) acc += phi_at(i, j) * m[static_cast<size_t>(j) * rows + k];
+        m2[static_cast<size_t>(i) * rows + k] = acc;
+      }
+    m.swap(m2);
+  }
+  if (!converged) return 0;
+  Mat p(static_cast<size_t>(n) * n, 0.0), phi(static_cast<size_t>(n) * n);
+  for (int i = 0; i < n; ++i) {
+    p[static_cast<size_t>(i) * n + i] = 1.0;
+    for (int j = 0; j < n; ++j) phi[static_cast<size_t>(i) * n + j] = phi_at(i, j);
+  }
+  const double tol = 1.0 / 16777216.0;
+  for (int w = 0; w <= 4096; ++w) {
+    double err = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      double acc = 0.0;
+      for (int i = 0; i < n; ++i) {
+        double e = 0.0;
+        for (int j = 0; j < n; ++j) e += std::fabs(p[static_cast<size_t>(i) * n + j]) * b[static_cast<size_t>(j)];
+        acc += std::fabs(cs.o[static_cast<size_t>(r) * ld + i]) * e;
+      }
+      err = acc > err ? acc : err;
+    }
+    if (err <= tol) return w < 1 ? 1 : w;
+    p = mat_mul(phi, p, n);
+  }
+  return 0;
+}
+
 int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp) {
   mp = LtiMmaPlan{};
   LtiChunkSystem cs;
@@ -593,6 +658,7 @@ int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp) {
   mp.kpad = kpad;
   mp.states = ks;
   mp.ok = 1;
+  mp.warm_chunks = lti_warm_chunks(cs);
   return DSPB200_OK;
 }
 
@@ -608,6 +674,45 @@ bool lti_mma_possible(const LtiMmaPlan& mp, const float* x, int64_t xs, const fl
 
 int lti_mma_chunk() { return kRows; }
 
+// How a batch is cut into work items (channel group x time slice) and what share of the SMs' time does useful work.
+//  * more groups than SMs: exact slices, a later slice picks up the end state its predecessor left (see the kernel);
+//  * fewer groups than SMs and `overlap` allowed: independent slices that start plan.warm_chunks early from a zero
+//    state, so a narrow batch (C2's 1024 channels: 8 groups) still fills the GPU, at the price of the warm-up.
+struct LtiSlicing { int64_t slices = 1; int warm = 0; double eff = 0.0; };
+static LtiSlicing lti_slicing(const LtiMmaPlan& mp, int64_t channels, int64_t n_out, bool overlap) {
+  const int64_t sms = sm_count(), n_tt = ceil_div(n_out, kRows), groups = ceil_div(channels, kTM);
+  LtiSlicing r;
+  if (groups > sms) {
+    // with at least one group per SM a slice's predecessor ran a whole round earlier, so its end state is waiting in
+    // memory; the smallest count that fills >= 95 % of the last round (or the best one up to 16)
+    for (int64_t h = 1; h <= 16 && ceil_div(n_tt, h) >= 8; ++h) {
+      const int64_t jobs = groups * ceil_div(n_tt, ceil_div(n_tt, h));
+      const double eff = static_cast<double>(jobs) / static_cast<double>(ceil_div(jobs, sms) * sms);
+      if (eff > r.eff + 1e-9) { r.eff = eff; r.slices = h; }
+      if (eff >= 0.95) break;
+    }
+    return r;
+  }
+  r.eff = static_cast<double>(groups) / static_cast<double>(sms);
+  if (!overlap || mp.warm_chunks <= 0 || getenv("DSPB200_EQ_NO_OVERLAP") != nullptr) return r;
+  const int64_t w = mp.warm_chunks;
+  for (int64_t h = 2; h <= 256 && ceil_div(n_tt, h) >= 8; ++h) {
+    const int64_t cpj = ceil_div(n_tt, h), hh = ceil_div(n_tt, cpj), jobs = groups * hh;
+    const int64_t rounds = ceil_div(jobs, sms);
+    // a round lasts as long as its longest item: cpj + w chunks; ideal: groups * n_tt chunks spread over all SMs
+    const double eff = static_cast<double>(groups * n_tt) / (static_cast<double>(sms * rounds) * static_cast<double>(cpj + w));
+    if (eff > r.eff + 1e-9) { r.eff = eff; r.slices = hh; r.warm = static_cast<int>(w); }
+  }
+  return r;
+}
+
+static bool buffers_overlap(const float* x, int64_t xs, const float* z, int64_t zs, int64_t channels) {
+  if (x == nullptr || z == nullptr) return false;
+  const uintptr_t x0 = reinterpret_cast<uintptr_t>(x), x1 = x0 + static_cast<uintptr_t>(channels * xs) * 4;
+  const uintptr_t z0 = reinterpret_cast<uintptr_t>(z), z1 = z0 + static_cast<uintptr_t>(channels * zs) * 4;
+  return x0 < z1 && z0 < x1;
+}
+
 bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs, int64_t channels,
                     int64_t n_in) {
   if (!mp.ok || reinterpret_cast<uintptr_t>(x) % 16 != 0 || xs % 4 != 0 || n_in < kRows) return false;
@@ -615,11 +720,14 @@ bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const floa
   if (mp.kpad != kNkb * kBK) return false;
   if (kSmemBytes + 2048 > static_cast<size_t>(max_smem_optin())) return false;
   if (getenv("DSPB200_EQ_FORCE_MMA") != nullptr) return true;
-  // a CTA walks a group of 128 channels through time: the form pays once the groups fill at least 80 % of the
-  // SMs (about 15k channels on 148 SMs); narrower batches stay on the FFMA scan kernel.  With more groups than
-  // SMs the time axis is cut in slices to even out the rounds (lti_mma_run).
+  // a CTA walks a group of 128 channels through time: the form pays once the work items keep the SMs about 80 % busy
+  // -- at least 0.8 groups per SM (about 15k channels on 148 SMs), or a narrower batch whose time axis is long enough
+  // to be cut into overlapping slices (out of place only: a slice re-reads the inputs before its own range); the
+  // FFMA scan kernel (47-50 % of the HBM roofline) serves the rest.
   const int64_t groups = ceil_div(channels, kTM), sms = sm_count();
-  return 5 * groups >= 4 * sms;
+  if (5 * groups >= 4 * sms) return true;
+  const LtiSlicing sl = lti_slicing(mp, channels, n_in, !buffers_overlap(x, xs, z, zs, channels));
+  return sl.warm > 0 && sl.eff >= 0.62;
 }
 
 int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int64_t zs, int64_t channels,
@@ -646,18 +754,11 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
   a.state_in = (state != nullptr && state_in) ? 1 : 0;
   memcpy(a.phi, mp.phi, sizeof(a.phi));
   const int64_t sms = sm_count();
-  // time slices per group: with at least one group per SM a slice's predecessor ran a whole round earlier, so its end
-  // state is waiting in memory; the smallest count that fills >= 95 % of the last round (or the best one up to 16)
-  int64_t slices = 1;
-  if (a.n_groups > sms) {
-    double best = 0.0;
-    for (int64_t h = 1; h <= 16 && ceil_div(a.n_tt, h) >= 8; ++h) {
-      const int64_t jobs = a.n_groups * ceil_div(a.n_tt, ceil_div(a.n_tt, h));
-      const double eff = static_cast<double>(jobs) / static_cast<double>(ceil_div(jobs, sms) * sms);
-      if (eff > best + 1e-9) { best = eff; slices = h; }
-      if (eff >= 0.95) break;
-    }
-  }
+  // exact hand-over slices for wide batches, overlapping warm-up slices for narrow ones (never in place, never in the
+  // streaming form, whose blocks reproduce one pass bit for bit)
+  const LtiSlicing sl = lti_slicing(mp, channels, n_out, state == nullptr && !buffers_overlap(x, xs, z, zs, channels));
+  int64_t slices = sl.slices;
+  a.warm = sl.warm;
   if (const char* e = getenv("DSPB200_EQ_SLICES")) {   // development: force the slice count
     const long v = atol(e);
     if (v >= 1 && v <= a.n_tt) slices = v;
@@ -678,7 +779,7 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
     cudaGetLastError();
   });
   const size_t flag_bytes = static_cast<size_t>(round_up((a.n_jobs + 1) * static_cast<int64_t>(sizeof(unsigned)), 256));
-  const size_t xfer_bytes = slices > 1 ? static_cast<size_t>(a.n_jobs) * mp.states * kTM * sizeof(float) : 0;
+  const size_t xfer_bytes = (slices > 1 && a.warm == 0) ? static_cast<size_t>(a.n_jobs) * mp.states * kTM * sizeof(float) : 0;
   unsigned char* scratch = nullptr;
   DSP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), flag_bytes + xfer_bytes, stream));
   DSP_CUDA(cudaMemsetAsync(scratch, 0, flag_bytes, stream));
@@ -706,8 +807,8 @@ int lti_mma_run(const LtiMmaPlan& mp, const float* x, int64_t xs, float* z, int6
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(prof);
     const double nt = h[2] ? static_cast<double>(h[2]) : 1.0;
-    fprintf(stderr, "lti_mma: %d CTAs, %lld groups x %lld slices; epilogue cycles per tile: waiting for the accumulator %.0f, tensor memory -> registers %.0f, state hand-over %.0f, clip + stores %.0f\n",
-            grid, static_cast<long long>(a.n_groups), static_cast<long long>(slices), h[0] / nt, h[1] / nt, h[3] / nt, h[4] / nt);
+    fprintf(stderr, "lti_mma: %d CTAs, %lld groups x %lld slices (warm-up %d chunks); epilogue cycles per tile: waiting for the accumulator %.0f, tensor memory -> registers %.0f, state hand-over %.0f, clip + stores %.0f\n",
+            grid, static_cast<long long>(a.n_groups), static_cast<long long>(slices), a.warm, h[0] / nt, h[1] / nt, h[3] / nt, h[4] / nt);
   }
   return rc;
 }

@@ -48,6 +48,10 @@ struct LtiMmaPlan {
   int states = 0;          // 2 * sections, padded to a multiple of 4
   float* d_table = nullptr;   // [hi, lo, free response][112][kpad]: rows 0..95 outputs, 96.. end states
   float phi[kLtiMaxStates * kLtiMaxStates] = {};   // state transition over one chunk
+  // chunks after which a slice started from a ZERO state is within 2^-24 of max|x| of the true output (the cascade
+  // forgets its past at the rate of its slowest pole); 0: not established.  Lets narrow batches cut the time axis
+  // into independent, overlapping slices (lti_mma_run).
+  int warm_chunks = 0;
 };
 // z = T x + O s, s' = Phi s + K x over `rows` samples (float64, host): tk [(rows + 16) x rows] = [T; K],
 // o [rows x 16], phi [16 x 16]; unused state rows/columns are zero.
@@ -60,6 +64,7 @@ void cascade_state_space(const Section* sec, int ns, std::vector<double>& A, std
                          std::vector<double>& C, double& D);
 int lti_mma_build_eq(const Section* sec, int ns, LtiMmaPlan& mp);
 void lti_mma_free(LtiMmaPlan& mp);
+int lti_warm_chunks(const LtiChunkSystem& cs);
 bool lti_mma_usable(const LtiMmaPlan& mp, const float* x, int64_t xs, const float* z, int64_t zs, int64_t channels,
                     int64_t n_in);
 // state (optional): [channels][16] floats in the plan's scaled basis, written with the state after the block;

@@ -222,6 +222,13 @@ class EqPlan:
                                                o.ctypes.data_as(pd), phi.ctypes.data_as(pd)))
         return tk[:r], tk[r:r + n], o[:, :n], phi[:n, :n]
 
+    def warm_chunks(self) -> int:
+        """96-sample chunks after which the cascade started from zero is within 2^-24 of max|x| of its true output
+        (the overlap of the tensor-core form's independent time slices on narrow batches); 0: no tensor form."""
+        k = C.c_int()
+        check(_lib.load().dspb200_eq_plan_warm_chunks(self._h, C.byref(k)))
+        return int(k.value)
+
     def describe(self) -> np.ndarray:
         n = C.c_int()
         buf = np.zeros((16, 9))

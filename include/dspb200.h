@@ -135,8 +135,13 @@ int dspb200_eq_plan_destroy(dspb200_eq_plan* plan);
  * over HBM for all sections.  In place (z == x) is allowed.  Two forms: the
  * chunked linear-recurrence scan on the FMA pipe (any dtype, any shape), and,
  * for fp32 batches wide enough to fill the GPU (about 15k channels; at most 8
- * sections; 16-byte aligned rows), the cascade as one linear system advanced 112
- * samples per tcgen05 GEMM tile with the state carried between tiles. */
+ * sections; 16-byte aligned rows), the cascade as one linear system advanced 96
+ * samples per tcgen05 GEMM tile with the state carried between tiles.  Narrower
+ * batches take the same form when the signal is long enough to be cut into
+ * independent time slices that fill the GPU (out of place only): a slice then
+ * starts dspb200_eq_plan_warm_chunks() chunks early from a zero state, by which
+ * time what the true state would add is below 2^-24 of max|x| -- inside float32
+ * rounding, not bit-identical to one sequential pass. */
 int dspb200_eq_run_f32(const dspb200_eq_plan* plan, const float* x, int64_t x_stride, float* z,
                        int64_t z_stride, int64_t channels, int64_t n, void* stream);
 int dspb200_eq_run_f64(const dspb200_eq_plan* plan, const double* x, int64_t x_stride, double* z,
@@ -170,6 +175,10 @@ int dspb200_eq_plan_kernel_kind(const dspb200_eq_plan* plan, int64_t channels, i
  * has no tensor form (no sections, or more than 8). */
 int dspb200_eq_plan_chunk_system(const dspb200_eq_plan* plan, int* rows, int* states, double* tk,
                                  double* o, double* phi);
+/* Introspection for tests (host only): the number of 96-sample chunks after which the cascade, started from a zero
+ * state, is within 2^-24 of max|x| of its true output -- the overlap with which the tensor-core form cuts the time
+ * axis of batches too narrow to fill the GPU into independent slices.  0: not established (no tensor form). */
+int dspb200_eq_plan_warm_chunks(const dspb200_eq_plan* plan, int* chunks);
 /* Introspection for tests: number of sections and, per section, 9 doubles
  * (a00 a01 a10 a11 b0 b1 c0 c1 d) of the state-space form the kernel runs. */
 int dspb200_eq_plan_describe(const dspb200_eq_plan* plan, int* n_sections, double* state_space,

@@ -242,3 +242,43 @@ def test_hann_by_angle_addition_matches_the_reference_window(n_fft):
     ref = o.hann_symmetric(n_fft)
     assert sorted(n.tolist()) == list(range(n_fft))
     assert np.max(np.abs(w.reshape(-1).astype(np.float64) - ref[n])) <= 2e-7
+
+
+@pytest.mark.parametrize("fs,gains", [(48000, (6, -3, 4, -6, 3, -9)), (48000, (15,) * 6), (48000, (-15,) * 6),
+                                      (48000, (0, 0, 0, 0, 0, 12)), (96000, (6, -3, 4, -6, 3, -9)), (8000, (15,) * 6)])
+def test_eq_warm_chunks_bound_holds(lib, fs, gains):
+    """Narrow batches run the tensor-core EQ on independent, overlapping time slices: a slice starts
+    plan.warm_chunks() chunks early from a ZERO state (csrc/eq_mma.cu, lti_warm_chunks).  Stepping the float64 chunk
+    system both ways -- from the true state and from zero -- the outputs must agree to 2^-24 of max|x| after the
+    warm-up, for worst-case-ish inputs too (a full-scale square wave at the slowest pole's frequency)."""
+    import dsp_audio_project_b200 as pk
+    plan = pk.EqPlan.from_gains(fs, gains_dict(gains), np.float32)
+    w = plan.warm_chunks()
+    T, K, O, Phi = plan.chunk_system()
+    L, S = T.shape[0], Phi.shape[0]
+    assert 1 <= w <= 4096
+    rho = np.max(np.abs(np.linalg.eigvals(Phi)))
+    assert rho ** w < 1e-3                                       # the slowest mode has decayed a good way
+    lead = 3 * w + 20
+    n = (lead + w + 12) * L
+    t = np.arange(n)
+    f_slow = 40.0 if gains[0] != 0 else 10000.0
+    for x in (np.random.default_rng(5).uniform(-1, 1, n), np.sign(np.sin(2 * np.pi * f_slow * t / fs) + 1e-9),
+              np.ones(n)):
+        X = x.reshape(-1, L)
+        s = np.zeros(S)
+        true_out = []
+        for k, xk in enumerate(X):
+            if k >= lead + w:
+                true_out.append(T @ xk + O @ s)
+            s = Phi @ s + K @ xk
+        s = np.zeros(S)
+        cold = []
+        for k in range(lead, len(X)):
+            if k >= lead + w:
+                cold.append(T @ X[k] + O @ s)
+            s = Phi @ s + K @ X[k]
+        err = np.max(np.abs(np.concatenate(true_out) - np.concatenate(cold)))
+        assert err <= 2.0 ** -24, (fs, gains, w, err)
+    # no tensor form, no bound
+    assert pk.EqPlan(48000, [], np.float32).warm_chunks() == 0
