@@ -357,13 +357,18 @@ template <> struct CtPlan<8192> { static constexpr int NP = 4; static constexpr 
 //            roundings deep) instead of 15 shared-memory reads; bit 1: Hann by angle addition instead
 //            of a table read per sample; bit 2: the last pass stores without padding (its stores and
 //            the epilogue's mirrored reads are unit-stride, the pad only costs them a 2-way conflict).
-template <typename T, int M, int R, int NS, int VAR>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `after_gather` runs in the LAST pass once the operands have left `tmp` for the butterfly registers: the caller's
+// chance to put the next item's loads in flight (into `tmp`) a whole pass before they are needed.
+template <typename T, int M, int R, int NS, int VAR, typename Hook>
 __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
-                                        const typename Cpx<T>::type* __restrict__ tw, const int t) {
+                                        const typename Cpx<T>::type* __restrict__ tw, const int t, Hook&& after_gather) {
   typedef typename Cpx<T>::type C;
   constexpr int Q = M / 16, B = 16 / R;
   C v[16];
   gather_butterflies<T, R>(v, tmp);
+  if constexpr (NS * R == M) after_gather();
 #pragma unroll
   for (int b = 0; b < B; ++b) {
     const int j = t + b * Q;
@@ -402,9 +407,10 @@ __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typena
   }
 }
 
-template <typename T, int M, int P, int NS, int VAR = 0>
+template <typename T, int M, int P, int NS, int VAR = 0, typename Hook = NoHook>
 __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
-                                          const typename Cpx<T>::type* tw, const int* tw_offset, const int t) {
+                                          const typename Cpx<T>::type* tw, const int* tw_offset, const int t,
+                                          Hook&& after_gather = Hook()) {
   typedef typename Cpx<T>::type C;
   if constexpr (P < CtPlan<M>::NP) {
     constexpr int R = CtPlan<M>::R[P];
@@ -420,9 +426,9 @@ __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename C
       }
       __syncthreads();
     }
-    ct_pass<T, M, R, NS, VAR>(tmp, s, tw + tw_offset[P], t);   // tw_offset: the table's own offsets (full or tree)
+    ct_pass<T, M, R, NS, VAR>(tmp, s, tw + tw_offset[P], t, after_gather);   // tw_offset: the table's own offsets (full or tree)
     __syncthreads();
-    ct_passes<T, M, P + 1, NS * R, VAR>(tmp, s, tw, tw_offset, t);
+    ct_passes<T, M, P + 1, NS * R, VAR>(tmp, s, tw, tw_offset, t, after_gather);
   }
 }
 
@@ -581,15 +587,24 @@ fft_fixed_kernel(const FftArgs<T> a) {
       }
     }
     __syncthreads();   // previous item's readers are done with s
-    ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t);
-    // the next item's loads fly while this item's epilogue reads shared memory
-    if (item + gridDim.x < a.n_items) {
-      if constexpr (kReal && !kSplit) {
-        fr_next += dfr;
-        c_next += dc;
-        if (fr_next >= a.n_frames) { fr_next -= a.n_frames; ++c_next; }
+    // the next item's loads are put in flight inside the last pass, as soon as its operands have left `tmp`: they
+    // have that pass's butterflies and the whole epilogue to land (issued after the passes they were still the
+    // hottest stall of the kernel: 12 % of its samples waiting on the first use of a frame)
+    auto prefetch = [&]() {
+      if (item + gridDim.x < a.n_items) {
+        if constexpr (kReal && !kSplit) {
+          fr_next += dfr;
+          c_next += dc;
+          if (fr_next >= a.n_frames) { fr_next -= a.n_frames; ++c_next; }
+        }
+        fetch(item + gridDim.x, tmp, c_next, fr_next);
       }
-      fetch(item + gridDim.x, tmp, c_next, fr_next);
+    };
+    if constexpr ((VAR & 16) != 0) {
+      ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t);
+      prefetch();
+    } else {
+      ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t, prefetch);
     }
     if constexpr (MODE == 0) {
       T* mg = a.mag + c * a.mag_channel_stride + fr * a.mag_frame_stride;
@@ -1231,7 +1246,7 @@ static int launch_stockham_t(FftArgs<T> a, cudaStream_t stream) {
 // (compact tables: 31 KB instead of 44 KB of shared memory per CTA at 4096 points, which leaves the L1 its
 // share of the SM's 256 KB), the angle-addition Hann and the unpadded last pass.  Measured on 4736 clips x
 // 480000 samples, 4096-point frames: 4.31 ms -> 3.37 ms.  DSPB200_FFT_VAR overrides it for the 4096-point
-// size (experiments: 0, 6, 7, 15).
+// size (experiments: 0, 6, 7, 15, 23).
 template <typename T, int MODE> struct FixedVar { static constexpr int value = (sizeof(T) == 4 && MODE == 0) ? 7 : 0; };
 
 template <typename T, int MODE, int M>
@@ -1243,7 +1258,7 @@ static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
     if (M == 2048) {
       const char* ev = getenv("DSPB200_FFT_VAR");
       if (ev) var = atoi(ev);
-      if (!(var == 0 || var == 6 || var == 7 || var == 15)) var = kVar;
+      if (!(var == 0 || var == 6 || var == 7 || var == 15 || var == 23)) var = kVar;
     }
     if (a.window != nullptr && a.hann_ab == nullptr) var = 0;
   }
@@ -1259,6 +1274,7 @@ static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
     if constexpr (M == 2048) {
       if (a.tw_in_smem && var == 6) kern = fft_fixed_kernel<T, MODE, M, true, 6>;
       if (a.tw_in_smem && var == 15) kern = fft_fixed_kernel<T, MODE, M, true, 15>;
+      if (a.tw_in_smem && var == 23) kern = fft_fixed_kernel<T, MODE, M, true, 23>;   // 7 with the next frame's loads issued after the passes
     }
   }
   DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
