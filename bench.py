@@ -332,9 +332,16 @@ def run_b200(args):
 
     # persistent device buffers so every step reuses the same memory.  Config C5 keeps z and the spectra; y is never
     # materialised: the fused kernel goes from x to z, the cascade writes y into z and equalises in place
-    x = torch.empty((clips, CLIP_SAMPLES), dtype=t_dt, device=dev)
-    z = torch.empty((clips, n_out), dtype=t_dt, device=dev)
-    mag = torch.empty((clips, n_frames, bins), dtype=t_dt, device=dev)
+    sched = None
+    if args.workload == "c5job":
+        # the job's waves go through the package's wave scheduler: two x buffers, the next wave generated on a side
+        # stream while the current wave's spectra are computed
+        sched = pkg.WaveScheduler(chain, clips, CLIP_SAMPLES, dev)
+        x, z, mag = sched.x[0], sched.z, sched.mag
+    else:
+        x = torch.empty((clips, CLIP_SAMPLES), dtype=t_dt, device=dev)
+        z = torch.empty((clips, n_out), dtype=t_dt, device=dev)
+        mag = torch.empty((clips, n_frames, bins), dtype=t_dt, device=dev)
     seed = 4 + rank                                      # seed 4 + rank
 
     def generate(first, count):
@@ -347,9 +354,7 @@ def run_b200(args):
         chain.run(x, z=z, mag=mag)
 
     def step_job():
-        for first, count in waves:
-            generate(first, count)
-            chain.run(x[:count], z=z[:count], mag=mag[:count])
+        sched.run(waves, lambda xv, first, count: pkg.generate_uniform(xv, seed, -0.5, 0.5, first_channel=first))
 
     def step_srceq():
         if kind == "fused":

@@ -11,7 +11,7 @@ spectrum, batched over channels, behind the reference's own function names.
 The CUDA library is the only compute path; nothing here falls back to the CPU.
 """
 from . import _lib  # noqa: F401
-from .plans import (Chain, EqPlan, FftPlan, SrcPlan, generate_uniform, mono_normalize,  # noqa: F401
+from .plans import (Chain, EqPlan, FftPlan, SrcPlan, WaveScheduler, generate_uniform, mono_normalize,  # noqa: F401
                     select_sections, src_geometry, to_pcm16)
 from .shard import channel_block, gather_spectra  # noqa: F401
 

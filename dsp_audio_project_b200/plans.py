@@ -509,6 +509,81 @@ class Chain:
         return z_pcm, peaks, mag
 
 
+class WaveScheduler:
+    """The C5 job as waves (wave pipelining with on-device generation; caller pattern
+    app.py:161-167 per clip).  A job of many clips is cut into waves that fit the GPU; wave k+1's input is PRODUCED on
+    a side stream (two x buffers) while wave k runs, so the producer -- the synthetic generator, a loader front end,
+    an H2D copy -- overlaps the spectra kernel instead of sitting between two waves.  (The fused SRC->EQ kernel owns
+    every SM's registers, so the producer's CTAs get onto the SMs when that kernel drains, i.e. next to the FFT, which
+    leaves a third of the HBM bandwidth unused.)
+
+        ws = WaveScheduler(chain, clips_per_wave, n_in, device)
+        ws.run(waves, produce, consume)      # waves: [(first_clip, count)], count <= clips_per_wave
+            produce(x_view, first, count)    # fills x_view [count, n_in]; runs under the side stream
+            consume(z_view, mag_view, first, count)   # optional; runs on the caller's stream after the wave
+
+    z and the spectra of a wave live in one buffer each: consume them (or copy them out) before the next wave's
+    kernels overwrite them -- the calls are stream-ordered, so a consume that only enqueues work is enough."""
+
+    def __init__(self, chain: "Chain", clips_per_wave: int, n_in: int, device):
+        torch = _torch()
+        self.chain = chain
+        self.clips = int(clips_per_wave)
+        self.n_in = int(n_in)
+        self.n_out = chain.out_len(self.n_in)
+        self.n_frames = self.n_out // chain.fft.n_fft
+        dt = torch.float32 if chain.dtype_id == F32 else torch.float64
+        self.device = torch.device(device)
+        pitch = -(-self.n_in // 4) * 4 if chain.dtype_id == F32 else -(-self.n_in // 2) * 2
+        self.x = [torch.empty((self.clips, pitch), dtype=dt, device=self.device)[:, :self.n_in] for _ in range(2)]
+        self.z = torch.empty((self.clips, self.n_out), dtype=dt, device=self.device)
+        self.mag = torch.empty((self.clips, self.n_frames, chain.fft.bins), dtype=dt, device=self.device)
+        self.side = torch.cuda.Stream(device=self.device)
+
+    def run(self, waves, produce, consume=None):
+        torch = _torch()
+        waves = list(waves)
+        if not waves:
+            return
+        if max(w[1] for w in waves) > self.clips:
+            raise ValueError("a wave is larger than clips_per_wave")
+        main = torch.cuda.current_stream(self.device)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]       # x[b] holds the wave produced into it
+        taken = [torch.cuda.Event(), torch.cuda.Event()]       # the kernels that read x[b] have been enqueued and run
+        start = torch.cuda.Event()
+        start.record(main)
+
+        def produce_into(b, first, count, after):
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(after)
+                produce(self.x[b][:count], first, count)
+                ready[b].record(self.side)
+
+        produce_into(0, waves[0][0], waves[0][1], start)
+        for i, (first, count) in enumerate(waves):
+            b = i & 1
+            main.wait_event(ready[b])
+            xv, zv, mv = self.x[b][:count], self.z[:count], self.mag[:count]
+            fused = (self.chain.dtype_id == F32 and self.chain.src is not None
+                     and self.chain.kernel_kind(count, self.n_in) == "fused")
+            if fused:
+                self.chain.run_fused(xv, out=zv)
+            elif self.chain.src is not None:
+                self.chain.src.run(xv, out=zv)
+                self.chain.eq.run(zv, out=zv)
+            else:
+                self.chain.eq.run(xv, out=zv)
+            taken[b].record(main)                              # x[b] is free once the kernels above have run
+            if i + 1 < len(waves):
+                # the next wave's producer: x[1 - b] was last read by wave i - 1 (already recorded), so it may start now
+                produce_into(1 - b, waves[i + 1][0], waves[i + 1][1], taken[1 - b] if i >= 1 else start)
+            if self.n_frames > 0:
+                self.chain.fft.magnitudes(zv, out=mv)
+            if consume is not None:
+                consume(zv, mv, first, count)
+        main.wait_stream(self.side)
+
+
 def to_pcm16(z, out=None):
     """Playback export of app.py:349-354 on [rows, time] CUDA tensors: nan_to_num,
     divide by the row peak when it is > 0, * 32767, truncate to int16.

@@ -445,7 +445,7 @@ def test_eq_tensor_core_form_matches_oracle_and_scan(pk, torch_cuda, gains, monk
         assert torch.equal(out[:, :n], z) and bool((out[:, n:] == 7.0).all())
         monkeypatch.delenv("DSPB200_EQ_FORCE_MMA")
     # the shape rule: wide batches take the tensor form on their own, narrow ones stay on the scan kernel
-    assert plan.kernel_kind(18944, 3000) == "tensor" and plan.kernel_kind(1024, 20000) == "scan"
+    assert plan.kernel_kind(18944, 3000) == "tensor" and plan.kernel_kind(1024, 2000) == "scan"
     x = torch.rand((18944, 3000), device="cuda", dtype=torch.float32) - 0.5
     z = plan.run(x)
     monkeypatch.setenv("DSPB200_EQ_NO_MMA", "1")
@@ -956,3 +956,38 @@ def test_eq_tensor_form_on_narrow_batches_overlapping_slices(pk, torch_cuda, mon
     assert plan.kernel_kind(1024, 20000) == "scan"            # too short to pay for the warm-up
     assert plan.kernel_kind(32, 480000) == "scan"             # a quarter of one group
     assert plan.kernel_kind(4096, 2880000) == "tensor"        # C3 slice
+
+
+def test_wave_scheduler_matches_wave_by_wave(pk, torch_cuda):
+    """pkg.WaveScheduler (the C5 job's waves, next wave produced on a side stream into the other x buffer): every wave's
+    z and spectra equal a plain Chain.run on the same clips, ragged last wave included; the producer sees each wave once."""
+    torch = torch_cuda
+    gd = gains_dict(C1_GAINS)
+    chain = pk.Chain(3, 2, 44100, gd, n_fft=1024, dtype=np.float32)
+    n_in, per = 9000, 6
+    waves = [(0, 6), (6, 6), (12, 6), (18, 3)]
+    ws = pk.WaveScheduler(chain, per, n_in, "cuda")
+    seen, got = [], {}
+
+    def produce(xv, first, count):
+        seen.append((first, count))
+        pk.generate_uniform(xv, 9, -0.5, 0.5, first_channel=first)
+
+    def consume(zv, mv, first, count):
+        got[first] = (zv.clone(), mv.clone())
+
+    for _ in range(2):                     # twice: the buffers and events are reused across jobs
+        seen.clear()
+        got.clear()
+        ws.run(waves, produce, consume)
+        torch.cuda.synchronize()
+        assert seen == waves
+        for first, count in waves:
+            x = torch.empty((count, n_in), dtype=torch.float32, device="cuda")
+            pk.generate_uniform(x, 9, -0.5, 0.5, first_channel=first)
+            _, z, mag = chain.run(x)
+            assert torch.equal(got[first][0], z) and torch.equal(got[first][1], mag), first
+    ref = o.chain(o.synthetic_clips(1, n_in, 9, -0.5, 0.5, first_channel=19)[0].astype(np.float64), 44100, 2, 3, gd,
+                  n_fft=1024, n_frames=4)
+    assert o.full_scale_err(got[18][0][1].cpu().numpy(), ref[1]) <= TOL_F32_EQ
+    assert o.rel_err(got[18][1][1, :4].cpu().numpy(), ref[2]) <= 1e-4

@@ -116,11 +116,20 @@ def main():
         # C3 slice: EQ six bands, 4096 ch x 2.88 M samples (of 65536 channels), both gain sets
         ch = 4096 if es == 4 else 2048
         x = (torch.rand((ch, 2_880_000), generator=gen, device=dev, dtype=tdt) - 0.5) * 0.5
+        z = torch.empty_like(x)          # out of place, as sistema_ecualizador is (y_n = x_n.copy(), dsp_core.py:230)
         for gname, gains in (("C1 gains", GAINS), ("all +15 dB", {k: 15 for k in GAINS})):
             eq = pkg.EqPlan.from_gains(48000, gains, ndt)
-            ms = timeit(lambda: eq.run(x, out=x), args.reps)
-            report(f"C3 slice EQ {ch}x2880000 {gname} {tag}", ms, x.numel(), 2 * es * x.numel())
-        del x
+            ms = timeit(lambda: eq.run(x, out=z), args.reps)
+            report(f"C3 slice EQ {ch}x2880000 {gname} {tag}", ms, x.numel(), 2 * es * x.numel(),
+                   {"kernel": eq.kernel_kind(ch, 2_880_000)})
+        del x, z
+        # C2-shaped EQ wave: 1024 channels x 10 s at 48 kHz (what the narrow-batch slicing of the tensor form is for)
+        x = (torch.rand((1024, 480000), generator=gen, device=dev, dtype=tdt) - 0.5) * 0.5
+        z = torch.empty_like(x)
+        eq = pkg.EqPlan.from_gains(48000, GAINS, ndt)
+        ms = timeit(lambda: eq.run(x, out=z), args.reps)
+        report(f"EQ 1024x480000 C1 gains {tag}", ms, x.numel(), 2 * es * x.numel(), {"kernel": eq.kernel_kind(1024, 480000)})
+        del x, z
         # C4 slice: 2^16-point frames of 2^20-sample clips, 512 channels (of 4096)
         ch = 512 if es == 4 else 256
         x = torch.rand((ch, 1 << 20), generator=gen, device=dev, dtype=tdt) * 2 - 1
