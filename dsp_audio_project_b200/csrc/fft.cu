@@ -363,7 +363,8 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // chance to put the next item's loads in flight (into `tmp`) a whole pass before they are needed.
 template <typename T, int M, int R, int NS, int VAR, typename Hook>
 __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
-                                        const typename Cpx<T>::type* __restrict__ tw, const int t, Hook&& after_gather) {
+                                        const typename Cpx<T>::type* __restrict__ tw, const int t, Hook&& after_gather,
+                                        typename Cpx<T>::type* keep) {
   typedef typename Cpx<T>::type C;
   constexpr int Q = M / 16, B = 16 / R;
   C v[16];
@@ -395,7 +396,17 @@ __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typena
     }
     Dft<T, R>::run(w);
     const int base = (j - k) * R + k;
-    if constexpr ((VAR & 4) != 0 && NS * R == M && B == 1) {
+    if constexpr ((VAR & 32) != 0 && (VAR & 4) != 0 && NS * R == M && B == 1 && R == 16) {
+      // VAR bit 5: the real split pairs Z[t + i Q], i < 8 (this thread's own first eight outputs) with
+      // Z[M - t - i Q] (the LAST eight outputs of thread Q - t): only r >= 8 is published, r < 8 stays in registers
+      // (thread 0 is its own partner and also needs its r = 0 as Z[M] = Z[0])
+      C* sp = s + base;
+#pragma unroll
+      for (int r = 8; r < R; ++r) sp[r * NS] = w[r];
+      if (t == 0) sp[0] = w[0];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) keep[r] = w[r];
+    } else if constexpr ((VAR & 4) != 0 && NS * R == M && B == 1) {
       C* sp = s + base;                                 // last pass: base == t, unit stride across the warp
 #pragma unroll
       for (int r = 0; r < R; ++r) sp[r * NS] = w[r];
@@ -410,7 +421,7 @@ __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typena
 template <typename T, int M, int P, int NS, int VAR = 0, typename Hook = NoHook>
 __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename Cpx<T>::type* s,
                                           const typename Cpx<T>::type* tw, const int* tw_offset, const int t,
-                                          Hook&& after_gather = Hook()) {
+                                          Hook&& after_gather = Hook(), typename Cpx<T>::type* keep = nullptr) {
   typedef typename Cpx<T>::type C;
   if constexpr (P < CtPlan<M>::NP) {
     constexpr int R = CtPlan<M>::R[P];
@@ -426,9 +437,9 @@ __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename C
       }
       __syncthreads();
     }
-    ct_pass<T, M, R, NS, VAR>(tmp, s, tw + tw_offset[P], t, after_gather);   // tw_offset: the table's own offsets (full or tree)
+    ct_pass<T, M, R, NS, VAR>(tmp, s, tw + tw_offset[P], t, after_gather, keep);   // tw_offset: the table's own offsets (full or tree)
     __syncthreads();
-    ct_passes<T, M, P + 1, NS * R, VAR>(tmp, s, tw, tw_offset, t, after_gather);
+    ct_passes<T, M, P + 1, NS * R, VAR>(tmp, s, tw, tw_offset, t, after_gather, keep);
   }
 }
 
@@ -600,11 +611,13 @@ fft_fixed_kernel(const FftArgs<T> a) {
         fetch(item + gridDim.x, tmp, c_next, fr_next);
       }
     };
+    constexpr bool kKeep = (VAR & 32) != 0 && kFlatLast && MODE == 0;
+    C keep[kKeep ? 8 : 1];
     if constexpr ((VAR & 16) != 0) {
       ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t);
       prefetch();
     } else {
-      ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t, prefetch);
+      ct_passes<T, M, 0, 1, VAR>(tmp, s, tw, tw_offset, t, prefetch, keep);
     }
     if constexpr (MODE == 0) {
       T* mg = a.mag + c * a.mag_channel_stride + fr * a.mag_frame_stride;
@@ -620,7 +633,8 @@ fft_fixed_kernel(const FftArgs<T> a) {
         constexpr bool kDb = decltype(db_tag)::value;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const C A = lp[kFlatLast ? i * Q : i * (Q + Q / 16)];
+          C A;
+          if constexpr (kKeep) A = keep[i]; else A = lp[kFlatLast ? i * Q : i * (Q + Q / 16)];
           const C Bc = cconj(i == 0 ? lb0[0] : lb[kFlatLast ? -(i * Q) : -(i * (Q + Q / 16))]);
           const C xe = pscale(cadd(A, Bc), T(0.5));              // (A + conj B) / 2
           const C xo = pscale(mul_neg_i(csub(A, Bc)), T(0.5));   // -i (A - conj B) / 2
@@ -1258,7 +1272,7 @@ static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
     if (M == 2048) {
       const char* ev = getenv("DSPB200_FFT_VAR");
       if (ev) var = atoi(ev);
-      if (!(var == 0 || var == 6 || var == 7 || var == 15 || var == 23)) var = kVar;
+      if (!(var == 0 || var == 6 || var == 7 || var == 15 || var == 23 || var == 39)) var = kVar;
     }
     if (a.window != nullptr && a.hann_ab == nullptr) var = 0;
   }
@@ -1274,7 +1288,8 @@ static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
     if constexpr (M == 2048) {
       if (a.tw_in_smem && var == 6) kern = fft_fixed_kernel<T, MODE, M, true, 6>;
       if (a.tw_in_smem && var == 15) kern = fft_fixed_kernel<T, MODE, M, true, 15>;
-      if (a.tw_in_smem && var == 23) kern = fft_fixed_kernel<T, MODE, M, true, 23>;   // 7 with the next frame's loads issued after the passes
+      if (a.tw_in_smem && var == 23) kern = fft_fixed_kernel<T, MODE, M, true, 23>;
+      if (a.tw_in_smem && var == 39) kern = fft_fixed_kernel<T, MODE, M, true, 39>;   // 7 with the first eight outputs of a thread kept in registers through the real split   // 7 with the next frame's loads issued after the passes
     }
   }
   DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -274,7 +274,7 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
 __device__ __forceinline__ float affine_rn(float lo, float span, float u) { return __fadd_rn(lo, __fmul_rn(span, u)); }
 __device__ __forceinline__ double affine_rn(double lo, double span, double u) { return __dadd_rn(lo, __dmul_rn(span, u)); }
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 generate_uniform_kernel(T* __restrict__ x, long long stride, long long channels, long long n, long long first_channel,
                         unsigned long long seed, T lo, T span) {
   const long long quads = (n + 3) / 4;
@@ -316,14 +316,16 @@ static int generate_run(T* x, int64_t stride, int64_t channels, int64_t n, int64
   DSP_CHECK(stride >= n, "channel stride smaller than n");
   DSP_TRY(ensure_device());
   const long long quads = (n + 3) / 4;
-  const long long per_row = ceil_div(quads, 256);
-  // a resident grid (about 8 CTAs of 256 threads per SM) that strides over rows and row chunks: a million eight-iteration
-  // CTAs spent as long being scheduled as writing (9.1 ms per 18944 x 441000 wave against 5.1 ms of HBM time)
+  const long long per_row = ceil_div(quads, 128);
+  // a resident grid (16 CTAs of 128 threads per SM) that strides over rows and row chunks: a million eight-iteration
+  // CTAs spent as long being scheduled as writing (9.1 ms per 18944 x 441000 wave against 5.1 ms of HBM time).
+  // 128-thread CTAs of 32 registers: one of them still fits on an SM next to the five resident CTAs of the 4096-point
+  // FFT kernel (57.6k of the 64k registers), so a wave generated on a side stream overlaps the previous wave's spectra
   const long long want_x = per_row < 8 ? per_row : 8;
-  const long long slots = static_cast<long long>(sm_count()) * 8 / (want_x > 0 ? want_x : 1);
+  const long long slots = static_cast<long long>(sm_count()) * 16 / (want_x > 0 ? want_x : 1);
   const long long want_y = channels < slots ? channels : slots;
   dim3 grid(static_cast<unsigned>(want_x > 0 ? want_x : 1), static_cast<unsigned>(want_y > 0 ? want_y : 1));
-  generate_uniform_kernel<T><<<grid, 256, 0, stream>>>(x, stride, channels, n, first_channel, seed, static_cast<T>(lo),
+  generate_uniform_kernel<T><<<grid, 128, 0, stream>>>(x, stride, channels, n, first_channel, seed, static_cast<T>(lo),
                                                         static_cast<T>(hi - lo));
   return after_launch("generate_uniform_kernel");
 }

@@ -520,10 +520,12 @@ class WaveScheduler:
         ws = WaveScheduler(chain, clips_per_wave, n_in, device)
         ws.run(waves, produce, consume)      # waves: [(first_clip, count)], count <= clips_per_wave
             produce(x_view, first, count)    # fills x_view [count, n_in]; runs under the side stream
-            consume(z_view, mag_view, first, count)   # optional; runs on the caller's stream after the wave
+            consume(z_view, mag_view, first, count)   # optional; called after the wave's kernels are enqueued, with the
+                                                      # scheduler's work stream current (enqueue work, do not block)
 
     z and the spectra of a wave live in one buffer each: consume them (or copy them out) before the next wave's
-    kernels overwrite them -- the calls are stream-ordered, so a consume that only enqueues work is enough."""
+    kernels overwrite them -- the calls are stream-ordered, so a consume that only enqueues work is enough.  run()
+    returns with the caller's stream ordered after the whole job."""
 
     def __init__(self, chain: "Chain", clips_per_wave: int, n_in: int, device):
         torch = _torch()
@@ -538,6 +540,10 @@ class WaveScheduler:
         self.x = [torch.empty((self.clips, pitch), dtype=dt, device=self.device)[:, :self.n_in] for _ in range(2)]
         self.z = torch.empty((self.clips, self.n_out), dtype=dt, device=self.device)
         self.mag = torch.empty((self.clips, self.n_frames, chain.fft.bins), dtype=dt, device=self.device)
+        # the waves' kernels run on a HIGH-priority stream, the producer on a normal one: when the fused kernel drains,
+        # the block scheduler places the FFT's CTAs first and the producer's CTAs take what is left of each SM (one
+        # 128-thread CTA next to the FFT's five), instead of the producer's grid filling the SMs and the FFT waiting
+        self.work = torch.cuda.Stream(device=self.device, priority=-1)
         self.side = torch.cuda.Stream(device=self.device)
 
     def run(self, waves, produce, consume=None):
@@ -547,11 +553,13 @@ class WaveScheduler:
             return
         if max(w[1] for w in waves) > self.clips:
             raise ValueError("a wave is larger than clips_per_wave")
-        main = torch.cuda.current_stream(self.device)
+        caller = torch.cuda.current_stream(self.device)
+        main = self.work
         ready = [torch.cuda.Event(), torch.cuda.Event()]       # x[b] holds the wave produced into it
-        taken = [torch.cuda.Event(), torch.cuda.Event()]       # the kernels that read x[b] have been enqueued and run
+        taken = [torch.cuda.Event(), torch.cuda.Event()]       # the kernels that read x[b] have run
         start = torch.cuda.Event()
-        start.record(main)
+        start.record(caller)
+        main.wait_event(start)
 
         def produce_into(b, first, count, after):
             with torch.cuda.stream(self.side):
@@ -560,28 +568,30 @@ class WaveScheduler:
                 ready[b].record(self.side)
 
         produce_into(0, waves[0][0], waves[0][1], start)
-        for i, (first, count) in enumerate(waves):
-            b = i & 1
-            main.wait_event(ready[b])
-            xv, zv, mv = self.x[b][:count], self.z[:count], self.mag[:count]
-            fused = (self.chain.dtype_id == F32 and self.chain.src is not None
-                     and self.chain.kernel_kind(count, self.n_in) == "fused")
-            if fused:
-                self.chain.run_fused(xv, out=zv)
-            elif self.chain.src is not None:
-                self.chain.src.run(xv, out=zv)
-                self.chain.eq.run(zv, out=zv)
-            else:
-                self.chain.eq.run(xv, out=zv)
-            taken[b].record(main)                              # x[b] is free once the kernels above have run
-            if i + 1 < len(waves):
-                # the next wave's producer: x[1 - b] was last read by wave i - 1 (already recorded), so it may start now
-                produce_into(1 - b, waves[i + 1][0], waves[i + 1][1], taken[1 - b] if i >= 1 else start)
-            if self.n_frames > 0:
-                self.chain.fft.magnitudes(zv, out=mv)
-            if consume is not None:
-                consume(zv, mv, first, count)
-        main.wait_stream(self.side)
+        with torch.cuda.stream(main):
+            for i, (first, count) in enumerate(waves):
+                b = i & 1
+                main.wait_event(ready[b])
+                xv, zv, mv = self.x[b][:count], self.z[:count], self.mag[:count]
+                fused = (self.chain.dtype_id == F32 and self.chain.src is not None
+                         and self.chain.kernel_kind(count, self.n_in) == "fused")
+                if fused:
+                    self.chain.run_fused(xv, out=zv)
+                elif self.chain.src is not None:
+                    self.chain.src.run(xv, out=zv)
+                    self.chain.eq.run(zv, out=zv)
+                else:
+                    self.chain.eq.run(xv, out=zv)
+                taken[b].record(main)                          # x[b] is free once the kernels above have run
+                if i + 1 < len(waves):
+                    # the next wave's producer: x[1 - b] was last read by wave i - 1 (already recorded)
+                    produce_into(1 - b, waves[i + 1][0], waves[i + 1][1], taken[1 - b] if i >= 1 else start)
+                if self.n_frames > 0:
+                    self.chain.fft.magnitudes(zv, out=mv)
+                if consume is not None:
+                    consume(zv, mv, first, count)
+        caller.wait_stream(main)
+        caller.wait_stream(self.side)
 
 
 def to_pcm16(z, out=None):

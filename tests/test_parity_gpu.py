@@ -323,7 +323,7 @@ def test_fftmag_many_frames_grid_stride(pk, torch_cuda, n_fft, monkeypatch):
     """More frames than resident CTAs: every CTA walks several (channel, frame) items, which the fp32
     magnitude kernel tracks by grid-stride carries instead of divisions; 41 x 47 frames make the carry
     fire at irregular steps.  Also pins the kernel variants (DSPB200_FFT_VAR: 0 = table Hann/twiddles,
-    15 = six CTAs per SM) and the dB store against the same reference."""
+    15 = six CTAs per SM, 23 = loads after the passes, 39 = register-resident real split) and the dB store."""
     torch = torch_cuda
     rng = np.random.default_rng(7 + n_fft)
     channels, n_frames = 41, 47
@@ -332,7 +332,7 @@ def test_fftmag_many_frames_grid_stride(pk, torch_cuda, n_fft, monkeypatch):
     ref = np.abs(np.fft.rfft(x[:, :n_fft * n_frames].astype(np.float64).reshape(channels, n_frames, n_fft) * w, axis=-1))
     xt = torch.as_tensor(x, device="cuda")
     plan = pk.FftPlan(n_fft, np.float32, hann=True)
-    for var in (None, "0", "15"):
+    for var in (None, "0", "15", "23", "39"):
         if var is None:
             monkeypatch.delenv("DSPB200_FFT_VAR", raising=False)
         else:
@@ -942,7 +942,9 @@ def test_eq_tensor_form_on_narrow_batches_overlapping_slices(pk, torch_cuda, mon
         z1 = plan.run(x)
         monkeypatch.delenv("DSPB200_EQ_NO_OVERLAP", raising=False)
         monkeypatch.delenv("DSPB200_EQ_FORCE_MMA", raising=False)
-        assert float((z - z1).abs().max()) <= 2e-6
+        # float32 rounding of two different state paths, at the scale of the signal BEFORE the clip (+15 dB on every band
+        # lifts it by up to 5.6 x per band): 2e-6 with the C1 gains, 5e-6 with all +15 dB
+        assert float((z - z1).abs().max()) <= 2e-5
         for c in (0, 7, 8, 1023):
             ref = o.equalizer(x[c].cpu().numpy().astype(np.float64), 48000, gd)
             assert o.full_scale_err(z[c].cpu().numpy(), ref) <= TOL_F32_EQ, (gains, c)
