@@ -29,6 +29,7 @@ SIGNATURES = {
     "dspb200_version": (C.c_int, []),
     "dspb200_last_error_string": (C.c_char_p, []),
     "dspb200_device_count": (C.c_int, [_pi]),
+    "dspb200_current_device": (C.c_int, [C.POINTER(C.c_int)]),
     "dspb200_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, _pi, _pi, _pi, C.POINTER(C.c_size_t)]),
     "dspb200_design_sinc_taps": (C.c_int, [C.c_double, C.c_int, _pd, C.c_int, _pi]),
     "dspb200_design_src_filter": (C.c_int, [C.c_int, C.c_int, _pd, C.c_int, _pi]),
@@ -42,6 +43,8 @@ SIGNATURES = {
     "dspb200_src_plan_kernel_kind": (C.c_int, [c_p, c_i64, c_i64, c_i64, _pi]),
     "dspb200_src_host_f32": (C.c_int, [C.c_int, C.c_int, c_p, c_i64, c_i64, c_p, c_i64, _pi64]),
     "dspb200_src_host_f64": (C.c_int, [C.c_int, C.c_int, c_p, c_i64, c_i64, c_p, c_i64, _pi64]),
+    "dspb200_src_plan_host_f32": (C.c_int, [c_p, c_p, c_i64, c_i64, c_p, c_i64, _pi64]),
+    "dspb200_src_plan_host_f64": (C.c_int, [c_p, c_p, c_i64, c_i64, c_p, c_i64, _pi64]),
     "dspb200_eq_plan_create": (C.c_int, [C.c_double, _pd, _pd, C.c_int, C.c_int, C.c_int, C.POINTER(c_p)]),
     "dspb200_eq_plan_create_raw": (C.c_int, [_pd, C.c_int, C.c_int, C.c_int, C.POINTER(c_p)]),
     "dspb200_eq_plan_create_bands": (C.c_int, [C.c_double, _pd, C.c_int, C.POINTER(c_p), _pi]),

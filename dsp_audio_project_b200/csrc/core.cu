@@ -157,6 +157,16 @@ int dspb200_device_count(int* count) {
   return DSPB200_OK;
 }
 
+int dspb200_current_device(int* device) {
+  DSP_CHECK(device != nullptr, "device is NULL");
+  *device = -1;
+  DSP_TRY(ensure_device());
+  int d = -1;
+  DSP_CUDA(cudaGetDevice(&d));
+  *device = d;
+  return DSPB200_OK;
+}
+
 int dspb200_device_info(int device, char* name, int name_len, int* sms, int* cc_major, int* cc_minor,
                         size_t* total_mem) {
   cudaDeviceProp prop;

@@ -610,18 +610,27 @@ static int plan_tables(dspb200_src_plan* p) {
   return DSPB200_OK;
 }
 
+// Host buffers through a plan the caller keeps (the drop-in module caches one per ratio and device) or, with
+// plan == NULL, through a plan built for the call.
 template <typename T>
-static int src_host(int L, int M, const T* x, int64_t channels, int64_t n_in, T* y, int64_t y_cap,
-                    int64_t* n_out_p) {
+static int src_host(const dspb200_src_plan* given, int L, int M, const T* x, int64_t channels, int64_t n_in, T* y,
+                    int64_t y_cap, int64_t* n_out_p) {
   DSP_CHECK(n_out_p != nullptr, "n_out is NULL");
   DSP_CHECK(channels >= 0 && n_in >= 1, "bad shape");
+  if (given) {
+    int dt = 0;
+    DSP_TRY(src_plan_ratio(given, &L, &M, &dt));
+    DSP_CHECK(dt == DType<T>::id, "plan dtype %d does not match the entry point", dt);
+  }
   int Tt; int64_t P, n_out;
   src_geometry(L, M, n_in, Tt, P, n_out);
   *n_out_p = n_out;
   DSP_CHECK(y_cap >= n_out, "y capacity %lld < %lld outputs", (long long)y_cap, (long long)n_out);
   if (channels == 0) return DSPB200_OK;
-  dspb200_src_plan* plan = nullptr;
-  DSP_TRY(dspb200_src_plan_create(L, M, DType<T>::id, &plan));
+  DSP_CHECK(x != nullptr && y != nullptr, "NULL buffer");
+  dspb200_src_plan* own = nullptr;
+  if (!given) DSP_TRY(dspb200_src_plan_create(L, M, DType<T>::id, &own));
+  const dspb200_src_plan* plan = given ? given : own;
   const int vec = 16 / static_cast<int>(sizeof(T));
   const int64_t xp = round_up(n_in, vec), yp = round_up(n_out, vec);
   T *dx = nullptr, *dy = nullptr;
@@ -636,7 +645,7 @@ static int src_host(int L, int M, const T* x, int64_t channels, int64_t n_in, T*
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   cudaFree(dx);
   cudaFree(dy);
-  dspb200_src_plan_destroy(plan);
+  if (own) dspb200_src_plan_destroy(own);
   if (e != cudaSuccess) return fail(DSPB200_ERR_CUDA, "src host path: %s", cudaGetErrorString(e));
   return rc;
 }
@@ -729,11 +738,21 @@ int dspb200_src_run_generic_f64(const dspb200_src_plan* plan, const double* x, i
 }
 int dspb200_src_host_f32(int L, int M, const float* x, int64_t channels, int64_t n_in, float* y,
                          int64_t y_cap, int64_t* n_out) {
-  return src_host<float>(L, M, x, channels, n_in, y, y_cap, n_out);
+  return src_host<float>(nullptr, L, M, x, channels, n_in, y, y_cap, n_out);
 }
 int dspb200_src_host_f64(int L, int M, const double* x, int64_t channels, int64_t n_in, double* y,
                          int64_t y_cap, int64_t* n_out) {
-  return src_host<double>(L, M, x, channels, n_in, y, y_cap, n_out);
+  return src_host<double>(nullptr, L, M, x, channels, n_in, y, y_cap, n_out);
+}
+int dspb200_src_plan_host_f32(const dspb200_src_plan* plan, const float* x, int64_t channels, int64_t n_in, float* y,
+                              int64_t y_cap, int64_t* n_out) {
+  DSP_CHECK(plan != nullptr, "NULL plan");
+  return src_host<float>(plan, 1, 1, x, channels, n_in, y, y_cap, n_out);
+}
+int dspb200_src_plan_host_f64(const dspb200_src_plan* plan, const double* x, int64_t channels, int64_t n_in, double* y,
+                              int64_t y_cap, int64_t* n_out) {
+  DSP_CHECK(plan != nullptr, "NULL plan");
+  return src_host<double>(plan, 1, 1, x, channels, n_in, y, y_cap, n_out);
 }
 
 }  // extern "C"

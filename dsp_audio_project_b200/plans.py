@@ -143,8 +143,9 @@ class SrcPlan:
         n_out = self.out_len(n_in)
         y = np.empty((ch, n_out), dtype=a.dtype)
         got = C.c_int64()
-        fn = _lib.load().dspb200_src_host_f32 if self.dtype_id == F32 else _lib.load().dspb200_src_host_f64
-        check(fn(self.L, self.M, a.ctypes.data, ch, n_in, y.ctypes.data, n_out, C.byref(got)))
+        # through THIS plan's tables (dspb200_src_host_* would build and drop a plan per call)
+        fn = _lib.load().dspb200_src_plan_host_f32 if self.dtype_id == F32 else _lib.load().dspb200_src_plan_host_f64
+        check(fn(self._h, a.ctypes.data, ch, n_in, y.ctypes.data, n_out, C.byref(got)))
         return y
 
 
@@ -313,13 +314,15 @@ class FftPlan:
         return int(b.value)
 
     def _workspace(self, n_transforms, device):
+        """Scratch of a long transform, taken per call from torch's stream-ordered caching allocator on the launch
+        stream: plans are shared between threads and streams (cached_fft_plan), a block kept on the plan would be."""
         torch = _torch()
         need = self.workspace_bytes(n_transforms)
         if need == 0:
-            return 0, 0
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws.data_ptr(), need
+            return None, 0, 0
+        with torch.cuda.device(device):
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return ws, ws.data_ptr(), need
 
     def n_frames(self, n: int, hop=None, offset: int = 0) -> int:
         hop = self.n_fft if hop is None else int(hop)
@@ -350,11 +353,12 @@ class FftPlan:
             out = torch.empty((ch, n_frames, self.bins), dtype=x.dtype, device=x.device)
         if tuple(out.shape) != (ch, n_frames, self.bins) or not out.is_contiguous():
             raise ValueError(f"out must be contiguous [{ch}, {n_frames}, {self.bins}]")
-        ws, ws_bytes = self._workspace(ch * n_frames, x.device)
+        ws_keep, ws, ws_bytes = self._workspace(ch * n_frames, x.device)
         fn = _lib.load().dspb200_fftmag_run_f32 if self.dtype_id == F32 else _lib.load().dspb200_fftmag_run_f64
         with torch.cuda.device(x.device):
             check(fn(self._h, x.data_ptr(), _row_stride(x), n_valid, int(offset), hop, n_frames, out.data_ptr(),
                      self.bins, n_frames * self.bins, ch, ws, ws_bytes, _stream_ptr(x)))
+        del ws_keep          # back to the allocator, ordered after the launch on this stream
         return out
 
     def magnitudes_host(self, x, *, hop=None, offset: int = 0, n_frames=None):
@@ -379,10 +383,11 @@ class FftPlan:
         batch = x.numel() // self.n_fft
         if out is None:
             out = torch.empty_like(x)
-        ws, ws_bytes = self._workspace(batch, x.device)
+        ws_keep, ws, ws_bytes = self._workspace(batch, x.device)
         fn = _lib.load().dspb200_fft_c2c_run_f32 if self.dtype_id == F32 else _lib.load().dspb200_fft_c2c_run_f64
         with torch.cuda.device(x.device):
             check(fn(self._h, x.data_ptr(), out.data_ptr(), batch, ws, ws_bytes, _stream_ptr(x)))
+        del ws_keep
         return out
 
     def c2c_host_f64(self, x):
@@ -458,14 +463,15 @@ class Chain:
         lib = _lib.load()
         check(lib.dspb200_chain_workspace_bytes(self.src._h if self.src else None, self.fft._h, ch, n_in,
                                                 int(keep_y), C.byref(need)))
-        if need.value and (self._ws is None or self._ws.numel() < need.value or self._ws.device != x.device):
-            self._ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
         fn = lib.dspb200_chain_run_f32 if self.dtype_id == F32 else lib.dspb200_chain_run_f64
         with torch.cuda.device(x.device):
+            # scratch of a long FFT: per call, from the stream-ordered allocator (a chain may be shared between streams)
+            ws = torch.empty(need.value, dtype=torch.uint8, device=x.device) if need.value else None
             check(fn(self.src._h if self.src else None, self.eq._h if self.eq else None, self.fft._h,
                      x.data_ptr(), _row_stride(x), ch, n_in, y.data_ptr() if y is not None else None,
-                     z.data_ptr(), mag.data_ptr(), self._ws.data_ptr() if need.value else None,
+                     z.data_ptr(), mag.data_ptr(), ws.data_ptr() if ws is not None else None,
                      need.value, _stream_ptr(x)))
+        del ws
         return y, z, mag
 
     def run_host(self, x, z=None, mag=None):
@@ -655,11 +661,27 @@ def generate_uniform(out, seed: int, lo: float = -0.5, hi: float = 0.5, first_ch
     return out
 
 
+def current_device() -> int:
+    """The CUDA device current on the calling thread (what a plan created now belongs to)."""
+    d = C.c_int(-1)
+    check(_lib.load().dspb200_current_device(C.byref(d)))
+    return int(d.value)
+
+
 @functools.lru_cache(maxsize=32)
-def cached_src_plan(L: int, M: int, dtype_id: int) -> SrcPlan:
+def _cached_src_plan(L: int, M: int, dtype_id: int, device: int) -> SrcPlan:
     return SrcPlan(L, M, _np_dtype(dtype_id))
 
 
 @functools.lru_cache(maxsize=32)
-def cached_fft_plan(n_fft: int, dtype_id: int, hann: bool) -> FftPlan:
+def _cached_fft_plan(n_fft: int, dtype_id: int, hann: bool, device: int) -> FftPlan:
     return FftPlan(n_fft, _np_dtype(dtype_id), hann)
+
+
+def cached_src_plan(L: int, M: int, dtype_id: int) -> SrcPlan:
+    """Plans own device tables: the cache is keyed by the current device as well."""
+    return _cached_src_plan(L, M, dtype_id, current_device())
+
+
+def cached_fft_plan(n_fft: int, dtype_id: int, hann: bool) -> FftPlan:
+    return _cached_fft_plan(n_fft, dtype_id, hann, current_device())

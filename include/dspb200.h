@@ -65,6 +65,9 @@ typedef struct dspb200_fft_plan dspb200_fft_plan;
 int dspb200_version(void);
 const char* dspb200_last_error_string(void);
 int dspb200_device_count(int* count);
+/* The CUDA device current on the calling thread: the device a plan created now belongs to (plans hold device
+ * tables; run entry points return DSPB200_ERR_INVALID when another device is current). */
+int dspb200_current_device(int* device);
 /* name_len bytes are written to name (NUL terminated). */
 int dspb200_device_info(int device, char* name, int name_len, int* sm_count,
                         int* cc_major, int* cc_minor, size_t* total_mem_bytes);
@@ -112,6 +115,12 @@ int dspb200_src_host_f32(int L, int M, const float* x, int64_t channels, int64_t
                          int64_t y_capacity_per_channel, int64_t* n_out);
 int dspb200_src_host_f64(int L, int M, const double* x, int64_t channels, int64_t n_in, double* y,
                          int64_t y_capacity_per_channel, int64_t* n_out);
+
+/* The same through a plan the caller keeps (its tap tables are built once, not per call). */
+int dspb200_src_plan_host_f32(const dspb200_src_plan* plan, const float* x, int64_t channels, int64_t n_in,
+                              float* y, int64_t y_capacity_per_channel, int64_t* n_out);
+int dspb200_src_plan_host_f64(const dspb200_src_plan* plan, const double* x, int64_t channels, int64_t n_in,
+                              double* y, int64_t y_capacity_per_channel, int64_t* n_out);
 
 /* ---- K2: biquad equaliser cascade (dsp_core.py:205-254) --------------- */
 /* Sections given as peaking (fc_eff, gain_db) pairs at rate fs, already
