@@ -69,7 +69,7 @@ SIGNATURES = {
     "dspb200_fftmag_host_f32": (C.c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_p]),
     "dspb200_fftmag_host_f64": (C.c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_p]),
     "dspb200_fft_c2c_host_f64": (C.c_int, [c_p, c_p, c_p, c_i64]),
-    "dspb200_chain_workspace_bytes": (C.c_int, [c_p, c_p, c_i64, c_i64, C.c_int, C.POINTER(C.c_size_t)]),
+    "dspb200_chain_workspace_bytes": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, C.c_int, C.POINTER(C.c_size_t)]),
     "dspb200_chain_run_f32": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
     "dspb200_chain_run_f64": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
     "dspb200_chain_kernel_kind": (C.c_int, [c_p, c_p, c_i64, c_i64, c_i64, _pi]),

@@ -83,6 +83,13 @@ static int chain_run(const dspb200_src_plan* src, const dspb200_eq_plan* eq, con
   unsigned char* wsp = static_cast<unsigned char*>(ws);
   const XzPlan* xp = nullptr;
   if (!y) DSP_TRY(chain_fused_plan<T>(src, eq, x, xs, z, s.n_out, channels, n_in, false, &xp));
+  if (!xp && !y && src && eq && sizeof(T) == 4 && ws != nullptr && ws_bytes >= static_cast<size_t>(round_up(static_cast<int64_t>(s.fft_ws), 256)) + s.y_bytes) {
+    // a narrow float32 batch whose equaliser runs the tensor-core form only out of place (overlapping time slices):
+    // the resampler writes into the scratch the caller provided behind the FFT's workspace
+    bool oop = false;
+    DSP_TRY(eq_prefers_out_of_place(eq, channels, s.n_out, s.n_out, &oop));
+    if (oop) y = reinterpret_cast<T*>(wsp + round_up(static_cast<int64_t>(s.fft_ws), 256));
+  }
   if (xp) {
     // SRC and EQ as one kernel: x is read once, z written once, y never exists (app.py:164-167)
     DSP_TRY(xz_run(*xp, reinterpret_cast<const float*>(x), xs, reinterpret_cast<float*>(z), s.n_out, channels, n_in, s.n_out,
@@ -244,8 +251,8 @@ using namespace dspb200;
 
 extern "C" {
 
-int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_fft_plan* fft, int64_t channels,
-                                  int64_t n_in, int keep_y, size_t* bytes) {
+int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_eq_plan* eq, const dspb200_fft_plan* fft,
+                                  int64_t channels, int64_t n_in, int keep_y, size_t* bytes) {
   DSP_CHECK(bytes != nullptr, "bytes is NULL");
   DSP_CHECK(channels >= 0 && n_in >= 1, "bad shape");
   int dtype = DSPB200_F32, L, M, nf;
@@ -254,8 +261,14 @@ int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_fft
   ChainShape s;
   if (dtype == DSPB200_F32) DSP_TRY(chain_shape<float>(src, fft, channels, n_in, s));
   else DSP_TRY(chain_shape<double>(src, fft, channels, n_in, s));
-  (void)keep_y;   // no y scratch any more: without a y buffer the resampler writes into z and the equaliser runs in place
+  // without a y buffer the resampler writes into z and the equaliser runs in place -- unless the batch is narrow enough
+  // that the equaliser's tensor-core form only pays out of place: then a y scratch rides behind the FFT's workspace
   *bytes = s.fft_ws;
+  if (!keep_y && dtype == DSPB200_F32 && src && eq) {
+    bool oop = false;
+    DSP_TRY(eq_prefers_out_of_place(eq, channels, s.n_out, s.n_out, &oop));
+    if (oop) *bytes = round_up(static_cast<int64_t>(s.fft_ws), 256) + s.y_bytes;
+  }
   return DSPB200_OK;
 }
 

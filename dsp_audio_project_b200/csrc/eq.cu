@@ -671,6 +671,21 @@ static int eq_mma_ready(const dspb200_eq_plan* plan, const float* x, int64_t xs,
   return DSPB200_OK;
 }
 
+// Does a float32 batch of this shape run the tensor-core form ONLY out of place?  (Narrow batches: the overlapping
+// time slices re-read inputs before their own range, so in place they fall back to the scan kernel.)  The chain then
+// gives the resampler's output a scratch buffer instead of equalising in place.
+int eq_prefers_out_of_place(const dspb200_eq_plan* plan, int64_t channels, int64_t n, int64_t stride, bool* prefers) {
+  *prefers = false;
+  if (plan == nullptr || plan->dtype != DSPB200_F32) return DSPB200_OK;
+  bool oop = false, inp = false;
+  DSP_TRY(eq_mma_ready(plan, nullptr, stride, nullptr, stride, channels, n, oop));
+  if (!oop) return DSPB200_OK;
+  const float* same = reinterpret_cast<const float*>(static_cast<uintptr_t>(256));   // any aligned pointer, used as x and z
+  DSP_TRY(eq_mma_ready(plan, same, stride, same, stride, channels, n, inp));
+  *prefers = !inp;
+  return DSPB200_OK;
+}
+
 template <typename T>
 int eq_run(const dspb200_eq_plan* plan, const T* x, int64_t xs, T* z, int64_t zs, int64_t channels,
            int64_t n, cudaStream_t stream) {

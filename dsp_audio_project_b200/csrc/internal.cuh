@@ -100,6 +100,7 @@ int xz_run(const XzPlan& xp, const float* x, int64_t xs, float* z, int64_t zs, i
 // fused form (other ratios, more than 8 sections, float64)
 int eq_plan_xz(const dspb200_eq_plan* eq, const dspb200_src_plan* src, const XzPlan** xp);
 int eq_plan_clip(const dspb200_eq_plan* plan);
+int eq_prefers_out_of_place(const dspb200_eq_plan* plan, int64_t channels, int64_t n, int64_t stride, bool* prefers);
 const std::vector<double>* src_plan_taps(const dspb200_src_plan* plan);
 int fft_plan_info(const dspb200_fft_plan* plan, int* n_fft, int* dtype);
 int eq_plan_dtype(const dspb200_eq_plan* plan);

@@ -461,8 +461,8 @@ class Chain:
             raise ValueError(f"mag must be a contiguous [{ch}, {n_frames}, {self.fft.bins}] tensor of x's dtype")
         need = C.c_size_t()
         lib = _lib.load()
-        check(lib.dspb200_chain_workspace_bytes(self.src._h if self.src else None, self.fft._h, ch, n_in,
-                                                int(keep_y), C.byref(need)))
+        check(lib.dspb200_chain_workspace_bytes(self.src._h if self.src else None, self.eq._h if self.eq else None,
+                                                self.fft._h, ch, n_in, int(keep_y), C.byref(need)))
         fn = lib.dspb200_chain_run_f32 if self.dtype_id == F32 else lib.dspb200_chain_run_f64
         with torch.cuda.device(x.device):
             # scratch of a long FFT: per call, from the stream-ordered allocator (a chain may be shared between streams)

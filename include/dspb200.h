@@ -248,9 +248,15 @@ int dspb200_fft_c2c_host_f64(const dspb200_fft_plan* plan, const double* in, dou
  * place.  The fused form needs |x| < 1023 (fp16 operand pieces); its stores
  * are clipped at 16-byte granularity, which never leaves a row of the dense
  * z (n_out % 4 == 0 is a condition of the form).
- * `workspace` only serves long FFTs (dspb200_fft_workspace_bytes). */
-int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_fft_plan* fft,
-                                  int64_t channels, int64_t n_in, int keep_y, size_t* bytes);
+ * `workspace` serves long FFTs (dspb200_fft_workspace_bytes) and, for float32
+ * batches too narrow to give every SM a channel group, a scratch for the
+ * resampler's output so that the equaliser can run its tensor-core form on
+ * overlapping time slices (out of place only); dspb200_chain_workspace_bytes
+ * says how much.  A smaller (or NULL) workspace is accepted when no long FFT
+ * needs it: the equaliser then runs in place. */
+int dspb200_chain_workspace_bytes(const dspb200_src_plan* src, const dspb200_eq_plan* eq,
+                                  const dspb200_fft_plan* fft, int64_t channels, int64_t n_in,
+                                  int keep_y, size_t* bytes);
 int dspb200_chain_run_f32(const dspb200_src_plan* src, const dspb200_eq_plan* eq,
                           const dspb200_fft_plan* fft, const float* x, int64_t x_stride,
                           int64_t channels, int64_t n_in, float* y, float* z, float* mag,

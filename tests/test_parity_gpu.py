@@ -6,6 +6,8 @@ Tolerances (north star): float64 kernels <= 1e-10 relative error
 FFT, <= 1e-4 of full scale for the EQ cascade.  Full scale is 1.0 for time
 signals and max|X| of the reference frame for spectra.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -993,3 +995,33 @@ def test_wave_scheduler_matches_wave_by_wave(pk, torch_cuda):
                   n_fft=1024, n_frames=4)
     assert o.full_scale_err(got[18][0][1].cpu().numpy(), ref[1]) <= TOL_F32_EQ
     assert o.rel_err(got[18][1][1, :4].cpu().numpy(), ref[2]) <= 1e-4
+
+
+def test_chain_c2_shaped_wave_uses_the_sliced_tensor_eq(pk, torch_cuda, monkeypatch):
+    """A 1024-clip wave (C2 / C5 shape, 8 channel groups): too narrow for the fused SRC->EQ kernel, so the chain runs
+    three kernels -- and gives the resampler's output a scratch buffer, so that the equaliser takes its tensor-core form
+    on overlapping time slices instead of the in-place scan kernel.  Oracle on two clips; same z as the in-place route
+    to float32 rounding; spectra tied to z by Parseval."""
+    torch = torch_cuda
+    gd = gains_dict(C1_GAINS)
+    ch = pk.Chain(160, 147, 44100, gd, n_fft=4096, dtype=np.float32)
+    clips, n_in = 1024, 441000
+    assert ch.kernel_kind(clips, n_in) == "cascade" and ch.eq.kernel_kind(clips, 480000) == "tensor"
+    need = C.c_size_t()
+    from dsp_audio_project_b200 import _lib
+    _lib.check(_lib.load().dspb200_chain_workspace_bytes(ch.src._h, ch.eq._h, ch.fft._h, clips, n_in, 0, C.byref(need)))
+    assert need.value >= clips * 480000 * 4                   # the y scratch
+    x = torch.empty((clips, n_in), dtype=torch.float32, device="cuda")
+    pk.generate_uniform(x, 4, -0.5, 0.5)
+    before = _lib.launch_count()
+    _, z, mag = ch.run(x)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - before == 3
+    for c in (0, 1023):
+        yo, zo, mo, _ = o.chain(x[c].cpu().numpy().astype(np.float64), 44100, 147, 160, gd, n_fft=4096, n_frames=2)
+        assert o.full_scale_err(z[c].cpu().numpy(), zo) <= TOL_F32_EQ
+        assert o.rel_err(mag[c, :2].cpu().numpy(), mo) <= 1e-4
+    monkeypatch.setenv("DSPB200_EQ_NO_OVERLAP", "1")          # in place, scan kernel
+    _, z2, _ = ch.run(x)
+    monkeypatch.delenv("DSPB200_EQ_NO_OVERLAP")
+    assert float((z - z2).abs().max()) <= 5e-6
