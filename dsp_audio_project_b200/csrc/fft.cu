@@ -36,13 +36,10 @@
 #include <vector>
 
 #include "common.cuh"
+#include "cpx.cuh"
 #include "internal.cuh"
 
 namespace dspb200 {
-
-template <typename T> struct Cpx;
-template <> struct Cpx<float> { typedef float2 type; };
-template <> struct Cpx<double> { typedef double2 type; };
 
 template <typename T> struct FftCfg;
 template <> struct FftCfg<float> { static constexpr int kSubMax = 8192; };
@@ -50,59 +47,6 @@ template <> struct FftCfg<double> { static constexpr int kSubMax = 4096; };
 
 constexpr int kPadShift = 4;  // one pad element per 16: conflict-free strided stores
 __host__ __device__ __forceinline__ int padded(int i) { return i + (i >> kPadShift); }
-
-template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
-template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
-template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
-  C r;
-  r.x = a.x * b.x - a.y * b.y;
-  r.y = a.x * b.y + a.y * b.x;
-  return r;
-}
-// float2 overloads: one complex number = one packed fp32 pair (FADD2 / FMUL2 / FFMA2);
-// ptxas folds the half swaps and sign flips of -i*z and of the complex product
-// into the instructions' operand modifiers.
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&r);
-}
-__device__ __forceinline__ float2 csub(float2 a, float2 b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&r);
-}
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {   // a * b = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
-  const float2 bs = make_float2(-b.y, b.x);
-  return ffma2s(bs, a.y, fmul2s(b, a.x));
-}
-__device__ __forceinline__ float2 pmul(float2 a, float2 b) {   // elementwise (a.x*b.x, a.y*b.y)
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&r);
-}
-__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
-__device__ __forceinline__ float2 pscale(float2 a, float s) { return fmul2s(a, s); }
-__device__ __forceinline__ double2 pscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {     // elementwise a*b + c
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
-  return *reinterpret_cast<float2*>(&r);
-}
-__device__ __forceinline__ double2 fma2(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
-template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
-template <typename C> __device__ __forceinline__ C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
-// magnitude (or its dB value) from |X|^2
-__device__ __forceinline__ double finish_mag(double v2, int db) {
-  const double m = sqrt(v2);
-  return db ? 20.0 * log10(m + 1e-12) : m;
-}
-__device__ __forceinline__ float finish_mag(float v2, int db) {
-  float m;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(v2));  // bare MUFU.SQRT (~1 ulp); |X|^2 < 1.2e-38 reads as 0
-  return db ? 20.0f * log10f(m + 1e-12f) : m;
-}
 
 // cos/sin(2 pi k / 16), k = 0..7
 __device__ constexpr double kCos16[8] = {1.0, 0.92387953251128673848, 0.70710678118654752440,
@@ -1042,6 +986,7 @@ struct dspb200_fft_plan {
   void* d_hann_ab = nullptr;   // on-the-fly Hann of the fixed-size kernel: per-thread (-cos/2, sin/2) pairs
   double hann_cos[16] = {0}, hann_sin[16] = {0};   // cos/sin(u * 2 pi 2Q/(N-1))
   void* d_tw_full = nullptr;   // W_N, for the direct small-size kernel
+  dspb200::FftR32Plan r32;     // 4096-point fp32 frames: the 32-points-per-thread kernel (fft_r32.cu)
 };
 
 namespace dspb200 {
@@ -1148,6 +1093,7 @@ static int plan_build(dspb200_fft_plan* p) {
     else if (rc != DSPB200_OK) return rc;
   }
   if (N < 32) DSP_TRY(upload_twiddles<T>(N, N, &p->d_tw_full));
+  if constexpr (sizeof(T) == 4) DSP_TRY(fft_r32_build(N, p->r32));
   {
     const int nc = N / 2;
     const int n1 = nc / kFsCols;
@@ -1400,6 +1346,13 @@ static int launch_four_step(const FftArgs<T>& a, const FourStep<T>& fs, long lon
   return after_launch("fft4_rows_kernel");
 }
 
+// 4096-point fp32 magnitude frames: DSPB200_FFT_VAR >= 64 selects the 32-points-per-thread kernel, a smaller value
+// the 16-points-per-thread variants of fft_fixed_kernel
+static bool fft_r32_selected() {
+  const char* ev = getenv("DSPB200_FFT_VAR");
+  return ev != nullptr && atoi(ev) >= 64;
+}
+
 template <typename T>
 int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_valid, int64_t offset, int64_t hop,
                int64_t n_frames, T* mag, int64_t mfs, int64_t mcs, int64_t channels, void* ws, size_t ws_bytes,
@@ -1436,6 +1389,10 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
   }
   fill_args(a, s);
   a.n_items = n_tr * s.r_top;
+  if constexpr (sizeof(T) == 4) {
+    if (p->r32.ok && fft_r32_selected())
+      return fft_r32_run(p->r32, x, xs, n_valid, offset, hop, n_frames, mag, mfs, mcs, channels, p->hann, p->db, stream);
+  }
   if (s.r_top == 1) return launch_stockham<T, 0>(a, stream);
   const size_t need = side_workspace(s, n_tr, sizeof(C));
   DSP_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
@@ -1600,6 +1557,7 @@ int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
   }
   cudaFree(p->d_window);
   cudaFree(p->d_hann_ab);
+  fft_r32_free(p->r32);
   cudaFree(p->d_tw_full);
   delete p;
   return DSPB200_OK;

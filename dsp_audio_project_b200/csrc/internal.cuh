@@ -19,6 +19,17 @@ template <typename T>
 int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_valid, int64_t offset,
                int64_t hop, int64_t n_frames, T* mag, int64_t mfs, int64_t mcs, int64_t channels,
                void* ws, size_t ws_bytes, cudaStream_t stream);
+// K3, 4096-point magnitude frames with 32 points per thread (fft_r32.cu).  fp32 only.
+struct FftR32Plan {
+  int ok = 0;
+  void* d_tables = nullptr;   // pass-1 twiddles, W_4096^t, per-thread Hann (A, B) pairs
+  float hann_cos[32] = {}, hann_sin[32] = {};
+};
+int fft_r32_build(int n_fft, FftR32Plan& rp);
+void fft_r32_free(FftR32Plan& rp);
+int fft_r32_run(const FftR32Plan& rp, const float* x, int64_t xs, int64_t n_valid, int64_t offset, int64_t hop,
+                int64_t n_frames, float* mag, int64_t mfs, int64_t mcs, int64_t channels, int hann, int db,
+                cudaStream_t stream);
 int src_plan_ratio(const dspb200_src_plan* plan, int* L, int* M, int* dtype);
 // playback export (post.cu; app.py:349-354): row peaks, then int16(trunc(nan_to_num(x) / peak * 32767))
 template <typename T>

@@ -13,7 +13,9 @@ import dsp_audio_project_b200 as pkg          # noqa: E402
 from oracle import dsp_oracle as o            # noqa: E402
 
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
-variants = sys.argv[2:] or ["0", "6", "7", "15"]     # "var[:cNN][:mK]": shared-memory carve-out %, CTA cap per SM
+# "var[:cNN][:mK][:gGB]": shared-memory carve-out %, CTA cap per SM, groups per CTA / CTAs per SM of the
+# 32-points-per-thread kernel (var >= 64)
+variants = sys.argv[2:] or ["0", "6", "7", "15"]
 n, n_fft = 480000, 4096
 torch.cuda.set_device(0)
 plan = pkg.FftPlan(n_fft, np.float32, hann=True)
@@ -35,8 +37,9 @@ for rnd in range(3):                       # interleaved rounds, best of each: t
         os.environ["DSPB200_FFT_VAR"] = parts[0]
         os.environ.pop("DSPB200_FFT_CARVEOUT", None)
         os.environ.pop("DSPB200_FFT_MAX_CTAS", None)
+        os.environ.pop("DSPB200_FFT_R32_CFG", None)
         for q in parts[1:]:
-            os.environ["DSPB200_FFT_CARVEOUT" if q[0] == "c" else "DSPB200_FFT_MAX_CTAS"] = q[1:]
+            os.environ[{"c": "DSPB200_FFT_CARVEOUT", "m": "DSPB200_FFT_MAX_CTAS", "g": "DSPB200_FFT_R32_CFG"}[q[0]]] = q[1:]
         m = plan.magnitudes(xs_d).cpu().numpy().astype(np.float64)
         err = float(np.max(np.abs(m - ref)) / np.max(np.abs(ref)))
         for _ in range(2):
