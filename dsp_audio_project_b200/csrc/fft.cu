@@ -1346,11 +1346,11 @@ static int launch_four_step(const FftArgs<T>& a, const FourStep<T>& fs, long lon
   return after_launch("fft4_rows_kernel");
 }
 
-// 4096-point fp32 magnitude frames: DSPB200_FFT_VAR >= 64 selects the 32-points-per-thread kernel, a smaller value
-// the 16-points-per-thread variants of fft_fixed_kernel
+// 4096-point fp32 magnitude frames run the 32-points-per-thread kernel (fft_r32.cu); DSPB200_FFT_VAR < 64 selects
+// the 16-points-per-thread variants of fft_fixed_kernel instead (7 = the best of them)
 static bool fft_r32_selected() {
   const char* ev = getenv("DSPB200_FFT_VAR");
-  return ev != nullptr && atoi(ev) >= 64;
+  return ev == nullptr || atoi(ev) >= 64;
 }
 
 template <typename T>

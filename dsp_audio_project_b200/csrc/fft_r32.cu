@@ -73,17 +73,21 @@ template <int R> struct Dft32 {
     Dft32<R / 2>::run(o);
 #pragma unroll
     for (int k = 0; k < R / 2; ++k) {
-      float2 t;
       if (k == 0) {
-        t = o[k];
+        v[k] = cadd(e[k], o[k]);
+        v[k + R / 2] = csub(e[k], o[k]);
       } else if (4 * k == R) {
-        t = mul_neg_i(o[k]);
+        const float2 t = mul_neg_i(o[k]);
+        v[k] = cadd(e[k], t);
+        v[k + R / 2] = csub(e[k], t);
       } else {
-        const float2 w = make_float2(static_cast<float>(kCos32[k * (32 / R)]), static_cast<float>(-kSin32[k * (32 / R)]));
-        t = cmul(w, o[k]);
+        // e + w o as two packed FMAs, e - w o = 2 e - (e + w o) as a third: 6 lane operations instead of 8
+        const float wr = static_cast<float>(kCos32[k * (32 / R)]), wi = static_cast<float>(-kSin32[k * (32 / R)]);
+        const float2 os = make_float2(-o[k].y, o[k].x);
+        const float2 lo = ffma2s(os, wi, ffma2s(o[k], wr, e[k]));
+        v[k] = lo;
+        v[k + R / 2] = ffma2s(e[k], 2.0f, make_float2(-lo.x, -lo.y));   // = twice_minus(e, lo), declared below
       }
-      v[k] = cadd(e[k], t);
-      v[k + R / 2] = csub(e[k], t);
     }
   }
 };
@@ -102,13 +106,23 @@ struct R32Args {
   float2 cc[32], ss[32];   // cos/sin(s * 2 pi 128/(N-1)), both halves alike
 };
 
+// c + a b with a's parts as broadcast scalars (two packed FMAs), and 2 e - lo (the other output of a butterfly whose
+// first output lo = e + t is known)
+__device__ __forceinline__ float2 cmadd(float2 a, float2 b, float2 c) {
+  return ffma2s(make_float2(-b.y, b.x), a.y, ffma2s(b, a.x, c));
+}
+__device__ __forceinline__ float2 twice_minus(float2 e, float2 lo) { return ffma2s(e, 2.0f, make_float2(-lo.x, -lo.y)); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 template <bool kDb> __device__ __forceinline__ float mag_of(float2 p) {
   return finish_mag(fmaf(p.x, p.x, p.y * p.y), kDb ? 1 : 0);
 }
 
-template <int G, int MINB>
+template <int G, int MINB, bool kPrefetch>
 __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw1 = reinterpret_cast<float2*>(smem_raw);
@@ -128,6 +142,17 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
 
   for (; item < a.n_items; item += stride) {
     float2 v[32];
+    long long cn = c + dc, frn = fr + dfr;                      // the group's next frame
+    if (frn >= a.n_frames) { frn -= a.n_frames; ++cn; }
+    if (kPrefetch && t == 0 && item + stride < a.n_items) {
+      // bring it into L2 while this one is transformed: the loads at the top of the next iteration are this kernel's
+      // longest stall (no registers to land them in early)
+      const long long fstart = a.offset + frn * a.hop;
+      if (fstart + kN <= a.n_valid) {
+        const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.x + cn * a.x_stride + fstart);
+        prefetch_l2_bulk(reinterpret_cast<const void*>(p0 & ~static_cast<uintptr_t>(15)), kN * 4 + ((p0 & 15) ? 16 : 0));
+      }
+    }
     {
       const float* xrow = a.x + c * a.x_stride;
       const long long fstart = a.offset + fr * a.hop;
@@ -168,7 +193,6 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) v[n1] = rp[n1 * 2 * kPitch];
     }
-    group_sync(bar);
     {
       // w^(a + 4 b) = w^a * w^(4 b): ten table entries, one rounding deep
       float2 wa[4], wb[8];
@@ -188,36 +212,40 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
     }
     Dft32<32>::run(v);
     {
-      float2* wp = xb + warp * 1024 + lane;
+      // in place: thread (n0, k2) puts its k1-th output where it read its n1 = k1 input, so no other thread's
+      // operands are overwritten and no barrier is needed between the reads above and these stores.
+      // E[k2 + 32 k1] sits at row 2 k1, O[...] at row 2 k1 + 1, column k2.
+      float2* wp = xb + warp * kPitch + lane;
 #pragma unroll
-      for (int k1 = 0; k1 < 32; ++k1) wp[32 * k1] = v[k1];
+      for (int k1 = 0; k1 < 32; ++k1) wp[k1 * 2 * kPitch] = v[k1];
     }
     group_sync(bar);
     {
       float* mg = a.mag + c * a.mcs + fr * a.mfs;
-      const float2* E = xb;
-      const float2* O = xb + 1024;
-      auto quad = [&](int q, float2 vq, auto db_tag) {
+      // quad q = t + 64 i = k2 + 32 k1 with k2 = lane, k1 = warp + 2 i; its mirror 1024 - q has k2' = (32 - lane) & 31 and
+      // k1' = 31 - k1 (lane > 0) or (32 - k1) & 31 (lane == 0)
+      const float2* Eq0 = xb + 2 * kPitch * warp + lane;
+      const float2* Ej0 = lane ? xb + 2 * kPitch * (31 - warp) + 32 - lane : xb + 2 * kPitch * (32 - warp);
+      const float2* Ej00 = t == 0 ? xb : Ej0;                 // q = 0 is its own mirror
+      auto quad = [&](int q, float2 vq, const float2* pe, const float2* pj, auto db_tag) {
         constexpr bool kDb = decltype(db_tag)::value;
-        const int j = (1024 - q) & 1023;
-        const float2 Eq = E[q], Oq = O[q], Ej = E[j], Oj = O[j];
+        const float2 Eq = pe[0], Oq = pe[kPitch], Ej = pj[0], Oj = pj[kPitch];
         const float2 w = cmul(vq, vq);                        // W_2048^q
-        const float2 P = cmul(w, Oq), Qc = cmul(cconj(w), Oj);
-        const float2 A = cadd(Eq, P), B2 = csub(Eq, P);       // Z[q], Z[1024 + q]
-        const float2 B = cadd(Ej, Qc), A2 = csub(Ej, Qc);     // Z[2048 - q], Z[1024 - q]
+        const float2 A = cmadd(w, Oq, Eq), B2 = twice_minus(Eq, A);           // Z[q], Z[1024 + q]
+        const float2 B = cmadd(cconj(w), Oj, Ej), A2 = twice_minus(Ej, B);    // Z[2048 - q], Z[1024 - q]
         {
           const float2 Bc = cconj(B);
           const float2 S = cadd(A, Bc), D = csub(A, Bc);
-          const float2 T = cmul(make_float2(vq.y, -vq.x), D);   // -i W_4096^q (A - conj B)
-          mg[q] = mag_of<kDb>(cadd(S, T));
-          mg[kM - q] = mag_of<kDb>(csub(S, T));
+          const float2 X1 = cmadd(make_float2(vq.y, -vq.x), D, S);   // S - i W_4096^q (A - conj B)
+          mg[q] = mag_of<kDb>(X1);
+          mg[kM - q] = mag_of<kDb>(twice_minus(S, X1));
         }
         {
           const float2 Bc = cconj(B2);
           const float2 S = cadd(A2, Bc), D = csub(A2, Bc);
-          const float2 T = cmul(make_float2(-vq.x, vq.y), D);   // -i W_4096^(1024-q) = -conj(W_4096^q)
-          mg[1024 - q] = mag_of<kDb>(cadd(S, T));
-          mg[1024 + q] = mag_of<kDb>(csub(S, T));
+          const float2 X1 = cmadd(make_float2(-vq.x, vq.y), D, S);   // -i W_4096^(1024-q) = -conj(W_4096^q)
+          mg[1024 - q] = mag_of<kDb>(X1);
+          mg[1024 + q] = mag_of<kDb>(twice_minus(S, X1));
         }
       };
       auto split = [&](auto db_tag) {
@@ -225,22 +253,22 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
         for (int i = 0; i < 8; ++i) {
           const float2 ci2 = make_float2(static_cast<float>(kW64r[i]), static_cast<float>(kW64i[i]));   // W_4096^(64 i)
           const float2 vq = i == 0 ? vt : cmul(vt, ci2);
-          quad(t + 64 * i, vq, db_tag);
+          quad(t + 64 * i, vq, Eq0 + 4 * kPitch * i, (i == 0 ? Ej00 : Ej0) - 4 * kPitch * i, db_tag);
         }
-        if (t == 0) quad(512, make_float2(0.70710678118654752440f, -0.70710678118654752440f), db_tag);
+        if (t == 0)
+          quad(512, make_float2(0.70710678118654752440f, -0.70710678118654752440f), xb + 32 * kPitch, xb + 32 * kPitch, db_tag);
       };
       if (a.db) split(std::true_type{}); else split(std::false_type{});
     }
     group_sync(bar);   // the split's readers are done with xb before the next frame's pass 0 writes it
-    fr += dfr;
-    c += dc;
-    if (fr >= a.n_frames) { fr -= a.n_frames; ++c; }
+    c = cn;
+    fr = frn;
   }
 }
 
-template <int G, int MINB>
+template <int G, int MINB, bool kPrefetch = true>
 int launch_r32(const R32Args& a, cudaStream_t stream) {
-  auto kern = fft4096_r32_kernel<G, MINB>;
+  auto kern = fft4096_r32_kernel<G, MINB, kPrefetch>;
   const size_t smem = static_cast<size_t>(kTw1 + G * kBuf) * sizeof(float2);
   DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 1;
@@ -312,16 +340,17 @@ int fft_r32_run(const FftR32Plan& rp, const float* x, int64_t xs, int64_t n_vali
     a.cc[s] = make_float2(rp.hann_cos[s], rp.hann_cos[s]);
     a.ss[s] = make_float2(rp.hann_sin[s], rp.hann_sin[s]);
   }
-  int cfg = 42;   // G = 4 groups per CTA, 2 CTAs per SM
+  int cfg = 81;   // G = 8 groups per CTA, 1 CTA per SM
   if (const char* ev = getenv("DSPB200_FFT_R32_CFG")) cfg = atoi(ev);
   switch (cfg) {
     case 24: return launch_r32<2, 4>(a, stream);
-    case 81: return launch_r32<8, 1>(a, stream);
+    case 42: return launch_r32<4, 2>(a, stream);
     case 61: return launch_r32<6, 1>(a, stream);
     case 32: return launch_r32<3, 2>(a, stream);
     case 33: return launch_r32<3, 3>(a, stream);
     case 52: return launch_r32<5, 2>(a, stream);
-    default: return launch_r32<4, 2>(a, stream);
+    case 810: return launch_r32<8, 1, false>(a, stream);
+    default: return launch_r32<8, 1>(a, stream);
   }
 }
 

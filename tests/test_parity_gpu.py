@@ -324,8 +324,9 @@ def test_fftmag_frames_vs_oracle(pk, torch_cuda, n_fft):
 def test_fftmag_many_frames_grid_stride(pk, torch_cuda, n_fft, monkeypatch):
     """More frames than resident CTAs: every CTA walks several (channel, frame) items, which the fp32
     magnitude kernel tracks by grid-stride carries instead of divisions; 41 x 47 frames make the carry
-    fire at irregular steps.  Also pins the kernel variants (DSPB200_FFT_VAR: 0 = table Hann/twiddles,
-    15 = six CTAs per SM, 23 = loads after the passes, 39 = register-resident real split) and the dB store."""
+    fire at irregular steps.  Also pins the kernel variants (DSPB200_FFT_VAR: unset / 64 = 32 points per thread at
+    4096 points (fft_r32.cu), 7 = the best 16-points-per-thread form, 0 = table Hann/twiddles, 15 = six CTAs per SM,
+    23 = loads after the passes, 39 = register-resident real split), the dB store and the rectangular window."""
     torch = torch_cuda
     rng = np.random.default_rng(7 + n_fft)
     channels, n_frames = 41, 47
@@ -334,7 +335,7 @@ def test_fftmag_many_frames_grid_stride(pk, torch_cuda, n_fft, monkeypatch):
     ref = np.abs(np.fft.rfft(x[:, :n_fft * n_frames].astype(np.float64).reshape(channels, n_frames, n_fft) * w, axis=-1))
     xt = torch.as_tensor(x, device="cuda")
     plan = pk.FftPlan(n_fft, np.float32, hann=True)
-    for var in (None, "0", "15", "23", "39"):
+    for var in (None, "64", "7", "0", "15", "23", "39"):
         if var is None:
             monkeypatch.delenv("DSPB200_FFT_VAR", raising=False)
         else:
@@ -350,6 +351,14 @@ def test_fftmag_many_frames_grid_stride(pk, torch_cuda, n_fft, monkeypatch):
     # 20*log10(1 + 1e-5 / 1e-2) = 8.7e-3 dB; log10f's own rounding is two orders below that
     loud = ref > 1e-2 * ref.max()
     assert np.max(np.abs(db - ref_db)[loud]) <= 20.0 * np.log10(1.0 + TOL_F32_FFT / 1e-2) + 1e-4
+    # no window, frames that overlap (hop < n_fft) and start at odd offsets, a tail frame padded with zeros
+    plain = pk.FftPlan(n_fft, np.float32, hann=False)
+    hop, off, nf = n_fft // 2 + 2, 1, 2 * n_frames - 1
+    m3 = plain.magnitudes(xt, hop=hop, offset=off, n_frames=nf).cpu().numpy()
+    xp = np.zeros((channels, off + hop * nf + n_fft)); xp[:, :x.shape[1]] = x
+    for f in (0, 1, nf // 2, nf - 2, nf - 1):
+        r3 = np.abs(np.fft.rfft(xp[:, off + f * hop:off + f * hop + n_fft], axis=-1))
+        assert o.rel_err(m3[:, f], r3) <= TOL_F32_FFT, f
 
 
 def test_fft_parseval_and_linearity_full_c4_frame_count(pk, torch_cuda):
