@@ -631,7 +631,11 @@ def run_b200(args):
         eq_kind = chain.eq.kernel_kind(clips, n_out)
         kernel_names = {"src": "src_mma_kernel" if src_kind == "tensor" else "src_tiled_kernel",
                         "eq": "lti_mma_kernel" if eq_kind == "tensor" else "eq_packed_kernel",
-                        "src_eq": "xz_mma_kernel", "fft": "fft_fixed_kernel"}
+                        "src_eq": "xz_mma_kernel",
+                        # float32 4096-point frames: 32 points per thread (csrc/fft_r32.cu) unless DSPB200_FFT_VAR < 64
+                        "fft": "fft4096_r32_kernel" if (args.dtype == "f32" and N_FFT == 4096 and
+                                                        int(os.environ.get("DSPB200_FFT_VAR", "64")) >= 64)
+                        else "fft_fixed_kernel"}
         kernels = {}
         for k in names:
             gbs = alg_bytes[k] / (per_kernel[k] * 1e-3) / 1e9

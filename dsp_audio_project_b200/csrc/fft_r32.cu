@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
       const float2* Eq0 = xb + 2 * kPitch * warp + lane;
       const float2* Ej0 = lane ? xb + 2 * kPitch * (31 - warp) + 32 - lane : xb + 2 * kPitch * (32 - warp);
       const float2* Ej00 = t == 0 ? xb : Ej0;                 // q = 0 is its own mirror
-      auto quad = [&](int q, float2 vq, const float2* pe, const float2* pj, auto db_tag) {
+      auto quad = [&](float* mq, float* mr, float2 vq, const float2* pe, const float2* pj, auto db_tag) {   // mq = mg + q, mr = mg - q
         constexpr bool kDb = decltype(db_tag)::value;
         const float2 Eq = pe[0], Oq = pe[kPitch], Ej = pj[0], Oj = pj[kPitch];
         const float2 w = cmul(vq, vq);                        // W_2048^q
@@ -237,26 +237,28 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
           const float2 Bc = cconj(B);
           const float2 S = cadd(A, Bc), D = csub(A, Bc);
           const float2 X1 = cmadd(make_float2(vq.y, -vq.x), D, S);   // S - i W_4096^q (A - conj B)
-          mg[q] = mag_of<kDb>(X1);
-          mg[kM - q] = mag_of<kDb>(twice_minus(S, X1));
+          mq[0] = mag_of<kDb>(X1);
+          mr[kM] = mag_of<kDb>(twice_minus(S, X1));
         }
         {
           const float2 Bc = cconj(B2);
           const float2 S = cadd(A2, Bc), D = csub(A2, Bc);
           const float2 X1 = cmadd(make_float2(-vq.x, vq.y), D, S);   // -i W_4096^(1024-q) = -conj(W_4096^q)
-          mg[1024 - q] = mag_of<kDb>(X1);
-          mg[1024 + q] = mag_of<kDb>(twice_minus(S, X1));
+          mr[1024] = mag_of<kDb>(X1);
+          mq[1024] = mag_of<kDb>(twice_minus(S, X1));
         }
       };
+      float* mlo = mg + t;
+      float* mhi = mg - t;
       auto split = [&](auto db_tag) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float2 ci2 = make_float2(static_cast<float>(kW64r[i]), static_cast<float>(kW64i[i]));   // W_4096^(64 i)
           const float2 vq = i == 0 ? vt : cmul(vt, ci2);
-          quad(t + 64 * i, vq, Eq0 + 4 * kPitch * i, (i == 0 ? Ej00 : Ej0) - 4 * kPitch * i, db_tag);
+          quad(mlo + 64 * i, mhi - 64 * i, vq, Eq0 + 4 * kPitch * i, (i == 0 ? Ej00 : Ej0) - 4 * kPitch * i, db_tag);
         }
         if (t == 0)
-          quad(512, make_float2(0.70710678118654752440f, -0.70710678118654752440f), xb + 32 * kPitch, xb + 32 * kPitch, db_tag);
+          quad(mg + 512, mg - 512, make_float2(0.70710678118654752440f, -0.70710678118654752440f), xb + 32 * kPitch, xb + 32 * kPitch, db_tag);
       };
       if (a.db) split(std::true_type{}); else split(std::false_type{});
     }
@@ -350,6 +352,9 @@ int fft_r32_run(const FftR32Plan& rp, const float* x, int64_t xs, int64_t n_vali
     case 33: return launch_r32<3, 3>(a, stream);
     case 52: return launch_r32<5, 2>(a, stream);
     case 810: return launch_r32<8, 1, false>(a, stream);
+    case 71: return launch_r32<7, 1>(a, stream);
+    case 91: return launch_r32<9, 1>(a, stream);
+    case 101: return launch_r32<10, 1>(a, stream);
     default: return launch_r32<8, 1>(a, stream);
   }
 }
