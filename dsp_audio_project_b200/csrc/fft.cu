@@ -987,6 +987,7 @@ struct dspb200_fft_plan {
   double hann_cos[16] = {0}, hann_sin[16] = {0};   // cos/sin(u * 2 pi 2Q/(N-1))
   void* d_tw_full = nullptr;   // W_N, for the direct small-size kernel
   dspb200::FftR32Plan r32;     // 4096-point fp32 frames: the 32-points-per-thread kernel (fft_r32.cu)
+  dspb200::FftLong32Plan l32;  // 2^16-point fp32 frames: three radix-32 passes in one launch (fft_long32.cu)
 };
 
 namespace dspb200 {
@@ -1093,7 +1094,10 @@ static int plan_build(dspb200_fft_plan* p) {
     else if (rc != DSPB200_OK) return rc;
   }
   if (N < 32) DSP_TRY(upload_twiddles<T>(N, N, &p->d_tw_full));
-  if constexpr (sizeof(T) == 4) DSP_TRY(fft_r32_build(N, p->r32));
+  if constexpr (sizeof(T) == 4) {
+    DSP_TRY(fft_r32_build(N, p->r32));
+    DSP_TRY(fft_long32_build(N, p->l32));
+  }
   {
     const int nc = N / 2;
     const int n1 = nc / kFsCols;
@@ -1393,6 +1397,13 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
     if (p->r32.ok && fft_r32_selected())
       return fft_r32_run(p->r32, x, xs, n_valid, offset, hop, n_frames, mag, mfs, mcs, channels, p->hann, p->db, stream);
   }
+  if constexpr (sizeof(T) == 4) {
+    // 2^16-point frames: DSPB200_FFT_LONG32=1 selects the three-pass form (fft_long32.cu) instead of the four-step kernels
+    const char* ev = getenv("DSPB200_FFT_LONG32");
+    if (p->l32.ok && ev != nullptr && atoi(ev) != 0)
+      return fft_long32_run(p->l32, x, xs, n_valid, offset, hop, n_frames, mag, mfs, mcs, channels, p->hann, p->db, ws,
+                            ws_bytes, stream);
+  }
   if (s.r_top == 1) return launch_stockham<T, 0>(a, stream);
   const size_t need = side_workspace(s, n_tr, sizeof(C));
   DSP_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
@@ -1558,6 +1569,7 @@ int dspb200_fft_plan_destroy(dspb200_fft_plan* p) {
   cudaFree(p->d_window);
   cudaFree(p->d_hann_ab);
   fft_r32_free(p->r32);
+  fft_long32_free(p->l32);
   cudaFree(p->d_tw_full);
   delete p;
   return DSPB200_OK;

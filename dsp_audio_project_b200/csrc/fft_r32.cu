@@ -27,73 +27,22 @@
 
 #include "common.cuh"
 #include "cpx.cuh"
+#include "fft_r32.cuh"
 #include "internal.cuh"
 
 namespace dspb200 {
 
 namespace {
 
+using namespace r32;
+
 constexpr int kN = 4096;          // real samples per frame
 constexpr int kM = 2048;          // complex points
 constexpr int kPitch = 33;        // exchange rows [64 threads][33]
 constexpr int kBuf = 64 * kPitch; // complex entries per group buffer (>= 2048)
-constexpr int kTw1Pitch = 11;     // [32][11]: w^1, w^2, w^3, w^4, w^8, ..., w^28, pad
-constexpr int kTw1 = 32 * kTw1Pitch;
 constexpr int kTabVt = kTw1;              // W_4096^t, t < 64
 constexpr int kTabHann = kTabVt + 64;     // per thread: (A(2t), A(2t+1)), (B(2t), B(2t+1))
 constexpr int kTabTotal = kTabHann + 128;
-
-// cos/sin(2 pi k / 32), k = 0..15
-__device__ constexpr double kCos32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
-                                          0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
-                                          0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
-                                          -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
-                                          -0.92387953251128675613, -0.98078528040323044913};
-__device__ constexpr double kSin32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
-                                          0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
-                                          0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
-                                          0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
-                                          0.38268343236508977173, 0.19509032201612826785};
-
-// W_64^i, i = 0..7
-__device__ constexpr double kW64r[8] = {1.0, 0.99518472667219688624, 0.98078528040323044913, 0.95694033573220886494,
-                                        0.92387953251128675613, 0.88192126434835502971, 0.83146961230254523708,
-                                        0.77301045336273696081};
-__device__ constexpr double kW64i[8] = {0.0, -0.09801714032956060199, -0.19509032201612826785, -0.29028467725446236764,
-                                        -0.38268343236508977173, -0.47139673682599764856, -0.55557023301960222474,
-                                        -0.63439328416364549822};
-
-// R-point DFT in registers, natural order in and out: the reference's even/odd recursion (dsp_core.py:52-66) unrolled.
-template <int R> struct Dft32 {
-  static __device__ __forceinline__ void run(float2* v) {
-    float2 e[R / 2], o[R / 2];
-#pragma unroll
-    for (int k = 0; k < R / 2; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
-    Dft32<R / 2>::run(e);
-    Dft32<R / 2>::run(o);
-#pragma unroll
-    for (int k = 0; k < R / 2; ++k) {
-      if (k == 0) {
-        v[k] = cadd(e[k], o[k]);
-        v[k + R / 2] = csub(e[k], o[k]);
-      } else if (4 * k == R) {
-        const float2 t = mul_neg_i(o[k]);
-        v[k] = cadd(e[k], t);
-        v[k + R / 2] = csub(e[k], t);
-      } else {
-        // e + w o as two packed FMAs, e - w o = 2 e - (e + w o) as a third: 6 lane operations instead of 8
-        const float wr = static_cast<float>(kCos32[k * (32 / R)]), wi = static_cast<float>(-kSin32[k * (32 / R)]);
-        const float2 os = make_float2(-o[k].y, o[k].x);
-        const float2 lo = ffma2s(os, wi, ffma2s(o[k], wr, e[k]));
-        v[k] = lo;
-        v[k + R / 2] = ffma2s(e[k], 2.0f, make_float2(-lo.x, -lo.y));   // = twice_minus(e, lo), declared below
-      }
-    }
-  }
-};
-template <> struct Dft32<1> {
-  static __device__ __forceinline__ void run(float2*) {}
-};
 
 struct R32Args {
   const float* x;
@@ -106,21 +55,7 @@ struct R32Args {
   float2 cc[32], ss[32];   // cos/sin(s * 2 pi 128/(N-1)), both halves alike
 };
 
-// c + a b with a's parts as broadcast scalars (two packed FMAs), and 2 e - lo (the other output of a butterfly whose
-// first output lo = e + t is known)
-__device__ __forceinline__ float2 cmadd(float2 a, float2 b, float2 c) {
-  return ffma2s(make_float2(-b.y, b.x), a.y, ffma2s(b, a.x, c));
-}
-__device__ __forceinline__ float2 twice_minus(float2 e, float2 lo) { return ffma2s(e, 2.0f, make_float2(-lo.x, -lo.y)); }
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-template <bool kDb> __device__ __forceinline__ float mag_of(float2 p) {
-  return finish_mag(fmaf(p.x, p.x, p.y * p.y), kDb ? 1 : 0);
-}
 
 template <int G, int MINB, bool kPrefetch>
 __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args a) {
@@ -193,23 +128,7 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) v[n1] = rp[n1 * 2 * kPitch];
     }
-    {
-      // w^(a + 4 b) = w^a * w^(4 b): ten table entries, one rounding deep
-      float2 wa[4], wb[8];
-#pragma unroll
-      for (int i = 1; i < 4; ++i) wa[i] = twr[i - 1];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) wb[i] = twr[2 + i];
-#pragma unroll
-      for (int n1 = 1; n1 < 32; ++n1) {
-        const int lo = n1 & 3, hi = n1 >> 2;
-        float2 w;
-        if (hi == 0) w = wa[lo];
-        else if (lo == 0) w = wb[hi];
-        else w = cmul(wa[lo], wb[hi]);
-        v[n1] = cmul(v[n1], w);
-      }
-    }
+    twiddle_powers(v, twr);   // W_1024^(n1 k2)
     Dft32<32>::run(v);
     {
       // in place: thread (n0, k2) puts its k1-th output where it read its n1 = k1 input, so no other thread's
@@ -299,10 +218,7 @@ int fft_r32_build(int n_fft, FftR32Plan& rp) {
     const long double ang = -2.0L * pi * num / den;
     return make_float2(static_cast<float>(cosl(ang)), static_cast<float>(sinl(ang)));
   };
-  for (int k2 = 0; k2 < 32; ++k2) {
-    for (int i = 1; i < 4; ++i) h[static_cast<size_t>(k2 * kTw1Pitch + i - 1)] = w(static_cast<long double>(k2) * i, 1024.0L);
-    for (int i = 1; i < 8; ++i) h[static_cast<size_t>(k2 * kTw1Pitch + 2 + i)] = w(static_cast<long double>(k2) * 4 * i, 1024.0L);
-  }
+  for (int k2 = 0; k2 < 32; ++k2) fill_twiddle_row(&h[static_cast<size_t>(k2 * kTw1Pitch)], k2, 1024.0L);
   for (int t = 0; t < 64; ++t) h[static_cast<size_t>(kTabVt + t)] = w(t, 4096.0L);
   // Hann sample n = 2(t + 64 s) + {0, 1}: w/2 = 1/4 + A cos(s D) + B sin(s D), A = -cos(phi_n0)/4, B = sin(phi_n0)/4,
   // phi_n = 2 pi n/(N-1), D = 2 pi 128/(N-1)  (dsp_core.py:87 with the real split's 1/2 folded in)

@@ -30,6 +30,18 @@ void fft_r32_free(FftR32Plan& rp);
 int fft_r32_run(const FftR32Plan& rp, const float* x, int64_t xs, int64_t n_valid, int64_t offset, int64_t hop,
                 int64_t n_frames, float* mag, int64_t mfs, int64_t mcs, int64_t channels, int hann, int db,
                 cudaStream_t stream);
+// K3, 2^16-point magnitude frames as three radix-32 passes (fft_long32.cu).  fp32 only.
+struct FftLong32Plan {
+  int ok = 0;
+  void* d_tables = nullptr;   // W_1024 powers, split twiddles, column twiddles, per-column Hann (A, B) pairs
+  float hann_cos[32] = {}, hann_sin[32] = {};
+};
+int fft_long32_build(int n_fft, FftLong32Plan& lp);
+void fft_long32_free(FftLong32Plan& lp);
+size_t fft_long32_workspace(int64_t n_transforms);
+int fft_long32_run(const FftLong32Plan& lp, const float* x, int64_t xs, int64_t n_valid, int64_t offset, int64_t hop,
+                   int64_t n_frames, float* mag, int64_t mfs, int64_t mcs, int64_t channels, int hann, int db, void* ws,
+                   size_t ws_bytes, cudaStream_t stream);
 int src_plan_ratio(const dspb200_src_plan* plan, int* L, int* M, int* dtype);
 // playback export (post.cu; app.py:349-354): row peaks, then int16(trunc(nan_to_num(x) / peak * 32767))
 template <typename T>
