@@ -1398,9 +1398,9 @@ int fftmag_run(const dspb200_fft_plan* p, const T* x, int64_t xs, int64_t n_vali
       return fft_r32_run(p->r32, x, xs, n_valid, offset, hop, n_frames, mag, mfs, mcs, channels, p->hann, p->db, stream);
   }
   if constexpr (sizeof(T) == 4) {
-    // 2^16-point frames: DSPB200_FFT_LONG32=1 selects the three-pass form (fft_long32.cu) instead of the four-step kernels
+    // 2^16-point frames run the three-pass form (fft_long32.cu); DSPB200_FFT_LONG32=0 selects the four-step kernels
     const char* ev = getenv("DSPB200_FFT_LONG32");
-    if (p->l32.ok && ev != nullptr && atoi(ev) != 0)
+    if (p->l32.ok && (ev == nullptr || atoi(ev) != 0))
       return fft_long32_run(p->l32, x, xs, n_valid, offset, hop, n_frames, mag, mfs, mcs, channels, p->hann, p->db, ws,
                             ws_bytes, stream);
   }

@@ -908,23 +908,49 @@ def test_library_reports_launches(pk):
     assert _lib.launch_count() > 0
 
 
-def test_long_fft_fused_four_step_form_matches(pk, torch_cuda, monkeypatch):
-    """The opt-in single-launch form of the 2^16-point transform (DSPB200_FFT_FUSED4=1: clusters of four CTAs keep the
-    four-step workspace in L2) gives the same spectra as the default two-kernel form, ragged tail included."""
+def test_long_fft_forms_match(pk, torch_cuda, monkeypatch):
+    """The forms of the 2^16-point transform give the same spectra, ragged tail included: the float32 default (three
+    radix-32 passes in one launch, csrc/fft_long32.cu), the two four-step kernels (DSPB200_FFT_LONG32=0; the float64
+    default) and their opt-in single-launch form (DSPB200_FFT_FUSED4=1: clusters of four CTAs keep the workspace in L2).
+    Also the rectangular window, an odd offset with overlapping frames, and the dB store of the three-pass form."""
     torch = torch_cuda
     rng = np.random.default_rng(65)
+    w = o.hann_symmetric(65536)
     for dt, tol in ((np.float32, TOL_F32_FFT), (np.float64, TOL_F64)):
         x = torch.as_tensor(rng.uniform(-1, 1, (5, 3 * 65536 + 1000)).astype(dt), device="cuda")
         plan = pk.FftPlan(65536, dt, hann=True)
-        monkeypatch.delenv("DSPB200_FFT_FUSED4", raising=False)
-        ref = plan.magnitudes(x, n_frames=4, n_valid=3 * 65536 + 1000).clone()     # the 4th frame is zero padded
-        monkeypatch.setenv("DSPB200_FFT_FUSED4", "1")
-        got = plan.magnitudes(x, n_frames=4, n_valid=3 * 65536 + 1000)
-        monkeypatch.delenv("DSPB200_FFT_FUSED4", raising=False)
-        assert float((got - ref).abs().max() / ref.abs().max()) <= 1e-6 if dt == np.float32 else 1e-14
-        w = o.hann_symmetric(65536)
-        want = np.abs(np.fft.rfft(x[2, 65536:2 * 65536].cpu().numpy().astype(np.float64) * w))
-        assert o.rel_err(got[2, 1].cpu().numpy(), want) <= tol
+        got = {}
+        for name, env in (("default", {}), ("four_step", {"DSPB200_FFT_LONG32": "0"}),
+                          ("fused4", {"DSPB200_FFT_LONG32": "0", "DSPB200_FFT_FUSED4": "1"})):
+            for k in ("DSPB200_FFT_LONG32", "DSPB200_FFT_FUSED4"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got[name] = plan.magnitudes(x, n_frames=4, n_valid=3 * 65536 + 1000).clone()   # the 4th frame is zero padded
+        for k in ("DSPB200_FFT_LONG32", "DSPB200_FFT_FUSED4"):
+            monkeypatch.delenv(k, raising=False)
+        ref = got["four_step"]
+        bound = 2e-6 if dt == np.float32 else 1e-14
+        for name in ("default", "fused4"):
+            assert float((got[name] - ref).abs().max() / ref.abs().max()) <= bound, (dt, name)
+        xh = x.cpu().numpy().astype(np.float64)
+        for name in got:
+            want = np.abs(np.fft.rfft(xh[2, 65536:2 * 65536] * w))
+            assert o.rel_err(got[name][2, 1].cpu().numpy(), want) <= tol, (dt, name)
+            tail = np.zeros(65536); tail[:1000] = xh[4, 3 * 65536:]
+            assert o.rel_err(got[name][4, 3].cpu().numpy(), np.abs(np.fft.rfft(tail * w))) <= tol, (dt, name)
+    # float32 three-pass form: no window, odd offset (misaligned loads), overlapping frames; dB spectra
+    x = torch.as_tensor(rng.uniform(-1, 1, (3, 2 * 65536 + 77)).astype(np.float32), device="cuda")
+    xh = x.cpu().numpy().astype(np.float64)
+    m = pk.FftPlan(65536, np.float32, hann=False).magnitudes(x, hop=32768 + 5, offset=3, n_frames=3).cpu().numpy()
+    xp = np.zeros((3, max(xh.shape[1], 3 + 2 * (32768 + 5) + 65536))); xp[:, :xh.shape[1]] = xh
+    for f in range(3):
+        s0 = 3 + f * (32768 + 5)
+        assert o.rel_err(m[:, f], np.abs(np.fft.rfft(xp[:, s0:s0 + 65536], axis=-1))) <= TOL_F32_FFT, f
+    db = pk.FftPlan(65536, np.float32, hann=True, db=True).magnitudes(x).cpu().numpy()
+    ref = np.abs(np.fft.rfft(xh[:, :2 * 65536].reshape(3, 2, 65536) * w, axis=-1))
+    loud = ref > 1e-2 * ref.max()
+    assert np.max(np.abs(db - 20.0 * np.log10(ref + 1e-12))[loud]) <= 20.0 * np.log10(1.0 + TOL_F32_FFT / 1e-2) + 1e-4
 
 
 def test_eq_tensor_form_on_narrow_batches_overlapping_slices(pk, torch_cuda, monkeypatch):
