@@ -141,15 +141,12 @@ __global__ void __launch_bounds__(kThreads, 1) fft65536_l32_kernel(const L32Args
         }
       }
       if (a.hann) {
-        const float2 ha = a.tables[kTabHann + 2 * n2], hb = a.tables[kTabHann + 2 * n2 + 1];
-        const float2 quarter = make_float2(0.25f, 0.25f);
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) v[n1] = pmul(v[n1], fma2(ha, a.cc[n1], fma2(hb, a.ss[n1], quarter)));
+        dft32_windowed(v, a.tables[kTabHann + 2 * n2], a.tables[kTabHann + 2 * n2 + 1], a.cc, a.ss);
       } else {
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) v[n1] = pscale(v[n1], 0.5f);
+        Dft32<32>::run(v);
       }
-      Dft32<32>::run(v);
       twiddle_powers(v, a.tables + kTabCol + n2 * 10);   // W_32768^(n2 k1)
       float2* wp = wsb + n2;
       float2* sp = rows + row_addr(n2);
@@ -166,9 +163,12 @@ __global__ void __launch_bounds__(kThreads, 1) fft65536_l32_kernel(const L32Args
       const long long cn = itn / a.n_frames, frn = itn - cn * a.n_frames;
       const long long fs2 = a.offset + frn * a.hop;
       if (fs2 + kN <= a.n_valid) {
-        const uintptr_t p0 = (reinterpret_cast<uintptr_t>(a.x + cn * a.x_stride + fs2) & ~static_cast<uintptr_t>(15)) +
-                             static_cast<uintptr_t>(T) * (kN * 4 / 16);
-        prefetch_l2_bulk(reinterpret_cast<const void*>(p0), kN * 4 / 16);
+        // sixteen pieces of whole 16-byte units INSIDE the frame only (the last piece of a misaligned frame is shorter)
+        const uintptr_t f0 = reinterpret_cast<uintptr_t>(a.x + cn * a.x_stride + fs2);
+        const uintptr_t p0 = ((f0 + 15) & ~static_cast<uintptr_t>(15)) + static_cast<uintptr_t>(T) * (kN * 4 / 16);
+        const uintptr_t end = (f0 + kN * 4) & ~static_cast<uintptr_t>(15);
+        const uintptr_t len = p0 + kN * 4 / 16 <= end ? kN * 4 / 16 : (end > p0 ? end - p0 : 0);
+        if (len) prefetch_l2_bulk(reinterpret_cast<const void*>(p0), static_cast<uint32_t>(len));
       }
     }
     // ---- step 2: rows, 16 per round (rows k1 and 32 - k1 in the same round; warp w owns slot w) ----
@@ -194,8 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) fft65536_l32_kernel(const L32Args
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = cp[j * 33];
-        twiddle_powers(v, twr);   // W_1024^(j ka)
-        Dft32<32>::run(v);
+        dft32_twiddled(v, twr);   // W_1024^(j ka) folded into the first butterfly level
 #pragma unroll
         for (int kb = 0; kb < 32; ++kb) cp[kb * 33] = v[kb];   // in place: Z_row[ka + 32 kb]
         if (lane == 0) rb[32 * 33] = v[0];                      // "element 1024" = element 0

@@ -57,7 +57,7 @@ struct R32Args {
 
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-template <int G, int MINB, bool kPrefetch>
+template <int G, int MINB, bool kPrefetch, bool kFold = true>
 __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw1 = reinterpret_cast<float2*>(smem_raw);
@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
       const long long fstart = a.offset + frn * a.hop;
       if (fstart + kN <= a.n_valid) {
         const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.x + cn * a.x_stride + fstart);
-        prefetch_l2_bulk(reinterpret_cast<const void*>(p0 & ~static_cast<uintptr_t>(15)), kN * 4 + ((p0 & 15) ? 16 : 0));
+        // whole 16-byte units INSIDE the frame only (a misaligned frame loses its first and last few bytes)
+        const uintptr_t p1 = (p0 + 15) & ~static_cast<uintptr_t>(15);
+        prefetch_l2_bulk(reinterpret_cast<const void*>(p1), static_cast<uint32_t>((p0 + kN * 4 - p1) & ~static_cast<uintptr_t>(15)));
       }
     }
     {
@@ -108,15 +110,18 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
         }
       }
     }
-    if (a.hann) {
+    if (a.hann && kFold) {
+      dft32_windowed(v, hann_a, hann_b, a.cc, a.ss);
+    } else if (a.hann) {
       const float2 quarter = make_float2(0.25f, 0.25f);
 #pragma unroll
       for (int s = 0; s < 32; ++s) v[s] = pmul(v[s], fma2(hann_a, a.cc[s], fma2(hann_b, a.ss[s], quarter)));
+      Dft32<32>::run(v);
     } else {
 #pragma unroll
       for (int s = 0; s < 32; ++s) v[s] = pscale(v[s], 0.5f);
+      Dft32<32>::run(v);
     }
-    Dft32<32>::run(v);
     {
       float2* wp = xb + t * kPitch;
 #pragma unroll
@@ -128,8 +133,12 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) v[n1] = rp[n1 * 2 * kPitch];
     }
-    twiddle_powers(v, twr);   // W_1024^(n1 k2)
-    Dft32<32>::run(v);
+    if constexpr (kFold) {
+      dft32_twiddled(v, twr);   // W_1024^(n1 k2) folded into the first butterfly level
+    } else {
+      twiddle_powers(v, twr);
+      Dft32<32>::run(v);
+    }
     {
       // in place: thread (n0, k2) puts its k1-th output where it read its n1 = k1 input, so no other thread's
       // operands are overwritten and no barrier is needed between the reads above and these stores.
@@ -187,9 +196,9 @@ __global__ void __launch_bounds__(64 * G, MINB) fft4096_r32_kernel(const R32Args
   }
 }
 
-template <int G, int MINB, bool kPrefetch = true>
+template <int G, int MINB, bool kPrefetch = true, bool kFold = true>
 int launch_r32(const R32Args& a, cudaStream_t stream) {
-  auto kern = fft4096_r32_kernel<G, MINB, kPrefetch>;
+  auto kern = fft4096_r32_kernel<G, MINB, kPrefetch, kFold>;
   const size_t smem = static_cast<size_t>(kTw1 + G * kBuf) * sizeof(float2);
   DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 1;
@@ -268,6 +277,7 @@ int fft_r32_run(const FftR32Plan& rp, const float* x, int64_t xs, int64_t n_vali
     case 33: return launch_r32<3, 3>(a, stream);
     case 52: return launch_r32<5, 2>(a, stream);
     case 810: return launch_r32<8, 1, false>(a, stream);
+    case 811: return launch_r32<8, 1, true, false>(a, stream);
     case 71: return launch_r32<7, 1>(a, stream);
     case 91: return launch_r32<9, 1>(a, stream);
     case 101: return launch_r32<10, 1>(a, stream);

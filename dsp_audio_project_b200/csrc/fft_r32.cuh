@@ -95,6 +95,76 @@ __device__ __forceinline__ void twiddle_powers(float2* v, const float2* __restri
   }
 }
 
+// The same 32-point DFT with its first butterfly level already done by the caller: P[i] = x_i + x_(i+16),
+// M[i] = x_i - x_(i+16), i < 16 (the leaves of the even/odd recursion pair inputs 16 apart).  Lets the caller fold a
+// per-input factor (window, twiddle) into that level: x_i f_i + x_j f_j is one multiply and one FMA, the difference
+// 2 x_i f_i - that sum a third instruction.
+template <int R> struct Dft32Pre {
+  static __device__ __forceinline__ void run(const float2* P, const float2* M, float2* v) {
+    float2 Pe[R / 4], Po[R / 4], Me[R / 4], Mo[R / 4], e[R / 2], o[R / 2];
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) { Pe[k] = P[2 * k]; Po[k] = P[2 * k + 1]; Me[k] = M[2 * k]; Mo[k] = M[2 * k + 1]; }
+    Dft32Pre<R / 2>::run(Pe, Me, e);
+    Dft32Pre<R / 2>::run(Po, Mo, o);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      if (k == 0) {
+        v[k] = cadd(e[k], o[k]);
+        v[k + R / 2] = csub(e[k], o[k]);
+      } else if (4 * k == R) {
+        const float2 t = mul_neg_i(o[k]);
+        v[k] = cadd(e[k], t);
+        v[k + R / 2] = csub(e[k], t);
+      } else {
+        const float wr = static_cast<float>(kCos32[k * (32 / R)]), wi = static_cast<float>(-kSin32[k * (32 / R)]);
+        const float2 os = make_float2(-o[k].y, o[k].x);
+        const float2 lo = ffma2s(os, wi, ffma2s(o[k], wr, e[k]));
+        v[k] = lo;
+        v[k + R / 2] = twice_minus(e[k], lo);
+      }
+    }
+  }
+};
+template <> struct Dft32Pre<2> {
+  static __device__ __forceinline__ void run(const float2* P, const float2* M, float2* v) { v[0] = P[0]; v[1] = M[0]; }
+};
+
+// v <- DFT32(v[n] f[n]) with real per-component factors f[n] = quarter + a cc[n] + b ss[n] (the Hann window by angle
+// addition: a, b per thread, cc / ss the step rotations duplicated into both halves)
+__device__ __forceinline__ void dft32_windowed(float2* v, float2 ha, float2 hb, const float2* cc, const float2* ss) {
+  const float2 quarter = make_float2(0.25f, 0.25f);
+  float2 P[16], M[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 wa = fma2(ha, cc[i], fma2(hb, ss[i], quarter));
+    const float2 wb = fma2(ha, cc[i + 16], fma2(hb, ss[i + 16], quarter));
+    const float2 t = pmul(v[i], wa);
+    P[i] = fma2(v[i + 16], wb, t);
+    M[i] = fma2(v[i + 16], make_float2(-wb.x, -wb.y), t);
+  }
+  Dft32Pre<32>::run(P, M, v);
+}
+
+// v <- DFT32(v[n] w^n) with the powers of w from a ten-entry row as in twiddle_powers
+__device__ __forceinline__ void dft32_twiddled(float2* v, const float2* __restrict__ row) {
+  float2 wa[4], wb[8];
+#pragma unroll
+  for (int i = 1; i < 4; ++i) wa[i] = row[i - 1];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) wb[i] = row[2 + i];
+  float2 P[16], M[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int lo = i & 3, hi = i >> 2;
+    const float2 wj = lo == 0 ? wb[hi + 4] : cmul(wa[lo], wb[hi + 4]);   // w^(i + 16)
+    float2 x = v[i];
+    if (i > 0) x = cmul(x, hi == 0 ? wa[lo] : (lo == 0 ? wb[hi] : cmul(wa[lo], wb[hi])));
+    P[i] = cmadd(wj, v[i + 16], x);
+    M[i] = twice_minus(x, P[i]);
+  }
+  Dft32Pre<32>::run(P, M, v);
+}
+
 // host: the ten entries of row `num/den` (w = exp(-2 pi i num/den))
 inline void fill_twiddle_row(float2* row, long double num, long double den) {
   const long double pi = 3.14159265358979323846264338327950288L;
