@@ -49,6 +49,15 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {     // el
   return *reinterpret_cast<float2*>(&r);
 }
 __device__ __forceinline__ double2 fma2(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+// c + a b, and 2 e - lo (the second output of a butterfly whose first output lo = e + t is known)
+__device__ __forceinline__ float2 cmadd(float2 a, float2 b, float2 c) {   // a's parts as broadcast scalars: two packed FMAs
+  return ffma2s(make_float2(-b.y, b.x), a.y, ffma2s(b, a.x, c));
+}
+__device__ __forceinline__ double2 cmadd(double2 a, double2 b, double2 c) {
+  return make_double2(fma(-a.y, b.y, fma(a.x, b.x, c.x)), fma(a.y, b.x, fma(a.x, b.y, c.y)));
+}
+__device__ __forceinline__ float2 twice_minus(float2 e, float2 lo) { return ffma2s(e, 2.0f, make_float2(-lo.x, -lo.y)); }
+__device__ __forceinline__ double2 twice_minus(double2 e, double2 lo) { return make_double2(fma(2.0, e.x, -lo.x), fma(2.0, e.y, -lo.y)); }
 template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
 template <typename C> __device__ __forceinline__ C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
 // magnitude (or its dB value) from |X|^2

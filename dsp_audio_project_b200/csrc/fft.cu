@@ -68,19 +68,22 @@ template <typename T, int R> struct Dft {
     Dft<T, R / 2>::run(o);
 #pragma unroll
     for (int k = 0; k < R / 2; ++k) {
-      C t;
       if (k == 0) {
-        t = o[k];
+        v[k] = cadd(e[k], o[k]);
+        v[k + R / 2] = csub(e[k], o[k]);
       } else if (4 * k == R) {
-        t = mul_neg_i(o[k]);
+        const C t = mul_neg_i(o[k]);
+        v[k] = cadd(e[k], t);
+        v[k + R / 2] = csub(e[k], t);
       } else {
+        // e + w o as FMAs onto e, e - w o = 2 e - (e + w o): 6 operations per butterfly instead of 8
         C w;
         w.x = static_cast<T>(kCos16[k * (16 / R)]);
         w.y = static_cast<T>(-kSin16[k * (16 / R)]);
-        t = cmul(w, o[k]);
+        const C lo = cmadd(w, o[k], e[k]);
+        v[k] = lo;
+        v[k + R / 2] = twice_minus(e[k], lo);
       }
-      v[k] = cadd(e[k], t);
-      v[k + R / 2] = csub(e[k], t);
     }
   }
 };

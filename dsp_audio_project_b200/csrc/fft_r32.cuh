@@ -62,12 +62,6 @@ template <> struct Dft32<1> {
   static __device__ __forceinline__ void run(float2*) {}
 };
 
-// c + a b with a's parts as broadcast scalars (two packed FMAs), and 2 e - lo (the other output of a butterfly whose
-// first output lo = e + t is known)
-__device__ __forceinline__ float2 cmadd(float2 a, float2 b, float2 c) {
-  return ffma2s(make_float2(-b.y, b.x), a.y, ffma2s(b, a.x, c));
-}
-__device__ __forceinline__ float2 twice_minus(float2 e, float2 lo) { return ffma2s(e, 2.0f, make_float2(-lo.x, -lo.y)); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
