@@ -322,7 +322,7 @@ __device__ __forceinline__ void ct_pass(const typename Cpx<T>::type* tmp, typena
     const int j = t + b * Q;
     const int k = j & (NS - 1);
     C* w = v + b * R;
-    if constexpr (NS > 1 && R == 16 && (VAR & 1) != 0 && sizeof(T) == 4) {
+    if constexpr (NS > 1 && R == 16 && (VAR & 1) != 0) {
       const C* row = tw + k * kTreePitch;
       const C w1 = row[0], w2 = row[1], w4 = row[2], w8 = row[3];
       const C w3 = cmul(w1, w2);
@@ -393,8 +393,10 @@ __device__ __forceinline__ void ct_passes(typename Cpx<T>::type* tmp, typename C
 template <typename T, int M, int VAR = 0> struct CtBounds {
   static constexpr int Q = M / 16;
   static constexpr int kThreads = (VAR & 8) ? 768 : 640;   // resident threads per SM aimed at
+  // float64: the product-tree form (VAR bit 0) holds 4 instead of 15 twiddles per pass in registers, so three CTAs fit
+  static constexpr int kThreads64 = (VAR & 1) ? 384 : 256;
   static constexpr int kMinBlocks = sizeof(T) == 4 ? (kThreads / Q > 0 ? (kThreads / Q > 16 ? 16 : kThreads / Q) : 1)
-                                                   : (256 / Q > 0 ? (256 / Q > 8 ? 8 : 256 / Q) : 1);
+                                                   : (kThreads64 / Q > 0 ? (kThreads64 / Q > 8 ? 8 : kThreads64 / Q) : 1);
 };
 
 template <typename T> __device__ __forceinline__ T mag_sqrt(T v) { return sqrt(v); }
@@ -417,7 +419,7 @@ fft_fixed_kernel(const FftArgs<T> a) {
   C* s = reinterpret_cast<C*>(smem_raw);
   const int t = threadIdx.x;
   C* stw = s + padded(M) + 1;
-  constexpr bool kTree = (VAR & 1) != 0 && sizeof(T) == 4;
+  constexpr bool kTree = (VAR & 1) != 0;
   const C* tw_src = kTree ? a.tw_tree : a.tw_pass;
   const int tw_count = kTree ? a.tw_tree_total : a.tw_total;
   const int* tw_offset = kTree ? a.tw_tree_offset : a.tw_offset;
@@ -1214,7 +1216,7 @@ static int launch_stockham_t(FftArgs<T> a, cudaStream_t stream) {
 // share of the SM's 256 KB), the angle-addition Hann and the unpadded last pass.  Measured on 4736 clips x
 // 480000 samples, 4096-point frames: 4.31 ms -> 3.37 ms.  DSPB200_FFT_VAR overrides it for the 4096-point
 // size (experiments: 0, 6, 7, 15, 23).
-template <typename T, int MODE> struct FixedVar { static constexpr int value = (sizeof(T) == 4 && MODE == 0) ? 7 : 0; };
+template <typename T, int MODE> struct FixedVar { static constexpr int value = MODE == 0 ? (sizeof(T) == 4 ? 7 : 5) : 0; };
 
 template <typename T, int MODE, int M>
 static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
@@ -1222,7 +1224,7 @@ static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
   constexpr int kVar = FixedVar<T, MODE>::value;
   int var = kVar;
   if constexpr (kVar != 0) {
-    if (M == 2048) {
+    if (M == 2048 && sizeof(T) == 4) {   // experiments of the float32 4096-point kernel only
       const char* ev = getenv("DSPB200_FFT_VAR");
       if (ev) var = atoi(ev);
       if (!(var == 0 || var == 6 || var == 7 || var == 15 || var == 23 || var == 39)) var = kVar;
@@ -1238,7 +1240,7 @@ static int launch_fixed(FftArgs<T> a, cudaStream_t stream) {
   if constexpr (kVar != 0) {
     if (var == kVar)
       kern = a.tw_in_smem ? fft_fixed_kernel<T, MODE, M, true, kVar> : fft_fixed_kernel<T, MODE, M, false, kVar>;
-    if constexpr (M == 2048) {
+    if constexpr (M == 2048 && sizeof(T) == 4) {
       if (a.tw_in_smem && var == 6) kern = fft_fixed_kernel<T, MODE, M, true, 6>;
       if (a.tw_in_smem && var == 15) kern = fft_fixed_kernel<T, MODE, M, true, 15>;
       if (a.tw_in_smem && var == 23) kern = fft_fixed_kernel<T, MODE, M, true, 23>;
