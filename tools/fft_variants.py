@@ -15,7 +15,7 @@ from oracle import dsp_oracle as o            # noqa: E402
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
 # "var[:cNN][:mK][:gGB]": shared-memory carve-out %, CTA cap per SM, groups per CTA / CTAs per SM of the
 # 32-points-per-thread kernel (var >= 64)
-variants = sys.argv[2:] or ["0", "6", "7", "15"]
+variants = sys.argv[2:] or ["0", "6", "7", "15", "64"]
 n, n_fft = 480000, 4096
 torch.cuda.set_device(0)
 plan = pkg.FftPlan(n_fft, np.float32, hann=True)
