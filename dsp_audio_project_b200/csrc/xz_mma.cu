@@ -54,6 +54,7 @@ constexpr int kWin = 114;           // window samples per chunk: the 113 a chunk
 constexpr int kNew = 74;            // samples read per chunk; consecutive windows start 73 (after an even chunk) or 74 apart
 constexpr int kAdv0 = 73, kAdv1 = 74;
 constexpr int kHalo = 40;
+static_assert(kNew == kWin - kHalo && kAdv1 == kNew && kAdv0 == kNew - 1, "window = carried halo + new samples");
 constexpr int kXSlots = 6;             // x boxes in shared memory (the converter holds up to four); further ahead the boxes are
 constexpr int kPrefetch = 0;            // prefetched into L2, so a landing only has to cover the L2 latency
 constexpr int kStages = 2;            // staging tiles of the TMA stores
