@@ -953,6 +953,33 @@ def test_long_fft_forms_match(pk, torch_cuda, monkeypatch):
     assert np.max(np.abs(db - 20.0 * np.log10(ref + 1e-12))[loud]) <= 20.0 * np.log10(1.0 + TOL_F32_FFT / 1e-2) + 1e-4
 
 
+def test_c4_many_transforms_parseval_and_spot_frames(pk, torch_cuda):
+    """A quarter of C4 (1024 channels x 2^20 samples: 16384 transforms of 2^16 points, float32): every persistent CTA of the
+    three-pass kernel reuses its workspace slot and row buffers over a hundred times.  Parseval of every frame against the
+    windowed time-domain energy (float64 on the device), and frames from the first, middle and last CTAs / iterations
+    against numpy."""
+    torch = torch_cuda
+    ch, n, nf = 1024, 1 << 20, 65536
+    x = torch.empty((ch, n), dtype=torch.float32, device="cuda")
+    pk.generate_uniform(x, 3, -1.0, 1.0)
+    mag = pk.FftPlan(nf, np.float32, hann=True).magnitudes(x)
+    assert tuple(mag.shape) == (ch, n // nf, nf // 2 + 1)
+    wh = o.hann_symmetric(nf)
+    w = torch.as_tensor(wh, device="cuda", dtype=torch.float64)
+    worst = 0.0
+    for c0 in range(0, ch, 128):
+        xf = x[c0:c0 + 128].view(128, n // nf, nf).double() * w
+        e_t = (xf * xf).sum(-1)
+        m = mag[c0:c0 + 128].double()
+        e_f = (m[..., 0] ** 2 + 2.0 * (m[..., 1:-1] ** 2).sum(-1) + m[..., -1] ** 2) / nf
+        worst = max(worst, float(((e_f - e_t).abs() / e_t).max()))
+        del xf, m
+    assert worst <= 1e-5, worst
+    for c, f in ((0, 0), (511, 7), (700, 3), (1023, 15)):
+        ref = np.abs(np.fft.rfft(x[c, f * nf:(f + 1) * nf].cpu().numpy().astype(np.float64) * wh))
+        assert o.rel_err(mag[c, f].cpu().numpy(), ref) <= TOL_F32_FFT, (c, f)
+
+
 def test_eq_tensor_form_on_narrow_batches_overlapping_slices(pk, torch_cuda, monkeypatch):
     """C2-shaped EQ (1024 channels x 10 s @ 48 kHz) fills the GPU by cutting the time axis into independent slices that
     start plan.warm_chunks() chunks early from a zero state (csrc/eq_mma.cu).  Against the float64 oracle on whole
