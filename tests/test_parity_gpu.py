@@ -953,6 +953,34 @@ def test_long_fft_forms_match(pk, torch_cuda, monkeypatch):
     assert np.max(np.abs(db - 20.0 * np.log10(ref + 1e-12))[loud]) <= 20.0 * np.log10(1.0 + TOL_F32_FFT / 1e-2) + 1e-4
 
 
+def test_c5_wave_frames_parseval_and_spot_frames(pk, torch_cuda):
+    """An eighth of the bench wave (2368 clips x 480000 samples: 277056 frames of 4096 points, float32) through the
+    32-points-per-thread kernel: every group walks ~230 (channel, frame) items by grid-stride carries.  Parseval of every
+    frame (float64 on the device), the dropped tail (480000 = 117 x 4096 + 768) and spot frames against numpy."""
+    torch = torch_cuda
+    ch, n, nf = 2368, 480000, 4096
+    x = torch.empty((ch, n), dtype=torch.float32, device="cuda")
+    pk.generate_uniform(x, 4, -1.0, 1.0)
+    plan = pk.FftPlan(nf, np.float32, hann=True)
+    mag = plan.magnitudes(x)
+    frames = n // nf
+    assert tuple(mag.shape) == (ch, frames, nf // 2 + 1)
+    wh = o.hann_symmetric(nf)
+    w = torch.as_tensor(wh, device="cuda", dtype=torch.float64)
+    worst = 0.0
+    for c0 in range(0, ch, 296):
+        xf = x[c0:c0 + 296, :frames * nf].reshape(296, frames, nf).double() * w
+        e_t = (xf * xf).sum(-1)
+        m = mag[c0:c0 + 296].double()
+        e_f = (m[..., 0] ** 2 + 2.0 * (m[..., 1:-1] ** 2).sum(-1) + m[..., -1] ** 2) / nf
+        worst = max(worst, float(((e_f - e_t).abs() / e_t).max()))
+        del xf, m
+    assert worst <= 1e-5, worst
+    for c, f in ((0, 0), (1, 116), (1183, 58), (2367, 116), (1500, 1)):
+        ref = np.abs(np.fft.rfft(x[c, f * nf:(f + 1) * nf].cpu().numpy().astype(np.float64) * wh))
+        assert o.rel_err(mag[c, f].cpu().numpy(), ref) <= TOL_F32_FFT, (c, f)
+
+
 def test_c4_many_transforms_parseval_and_spot_frames(pk, torch_cuda):
     """A quarter of C4 (1024 channels x 2^20 samples: 16384 transforms of 2^16 points, float32): every persistent CTA of the
     three-pass kernel reuses its workspace slot and row buffers over a hundred times.  Parseval of every frame against the
